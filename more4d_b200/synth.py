@@ -1,0 +1,138 @@
+"""Synthetic weights and inputs for the hot path (no checkpoints ship with the reference and
+there is no network — SURVEY.md F5).
+
+Every tensor is drawn from its own generator seeded by (seed, crc32(key)), so a single key
+can be regenerated anywhere (CPU for parity tests, CUDA for the bench) without materialising
+the rest.  Key names are the reference's state-dict keys so the same dict
+loads into the reference modules, the CPU oracle and the CUDA host mirror.
+
+The reference zero-initialises several layers (head.head.weight t4d:1390, the MPM's last
+linear and gate t4d:750-755, VAE AttentionBlock.proj vae:242, VAEEncoderadaptor.conv_out
+traj:170); all of them get non-zero values here, otherwise parity would be vacuous (F6).
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, Iterator, Tuple
+
+import torch
+
+from .config import DiTConfig
+
+
+def _gen(seed: int, key: str, device) -> torch.Generator:
+    g = torch.Generator(device=device)
+    g.manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFFFFFFFFFF)
+    return g
+
+
+def _randn(seed, key, shape, std, device, dtype, mean=0.0):
+    g = _gen(seed, key, device)
+    t = torch.randn(shape, generator=g, device=device, dtype=torch.float32) * std + mean
+    return t.to(dtype)
+
+
+def dit_param_specs(cfg: DiTConfig) -> Iterator[Tuple[str, tuple, float, float]]:
+    """Yield (key, shape, std, mean) for every parameter of the reference DiT."""
+    C, F = cfg.dim, cfg.ffn_dim
+    w = 0.02
+    pt, ph, pw = cfg.patch_size
+    yield "patch_embedding.weight", (C, cfg.in_dim, pt, ph, pw), 0.05, 0.0
+    yield "patch_embedding.bias", (C,), w, 0.0
+    yield "text_embedding.0.weight", (C, cfg.text_dim), w, 0.0
+    yield "text_embedding.0.bias", (C,), w, 0.0
+    yield "text_embedding.2.weight", (C, C), w, 0.0
+    yield "text_embedding.2.bias", (C,), w, 0.0
+    yield "time_embedding.0.weight", (C, cfg.freq_dim), w, 0.0
+    yield "time_embedding.0.bias", (C,), w, 0.0
+    yield "time_embedding.2.weight", (C, C), w, 0.0
+    yield "time_embedding.2.bias", (C,), w, 0.0
+    yield "time_projection.1.weight", (6 * C, C), w, 0.0
+    yield "time_projection.1.bias", (6 * C,), w, 0.0
+    for i in range(cfg.num_layers):
+        p = f"blocks.{i}."
+        yield p + "modulation", (1, 6, C), C ** -0.5, 0.0
+        for name in ("q", "k", "v", "o"):
+            yield p + f"self_attn.{name}.weight", (C, C), w, 0.0
+            yield p + f"self_attn.{name}.bias", (C,), w, 0.0
+        yield p + "self_attn.norm_q.weight", (C,), 0.1, 1.0
+        yield p + "self_attn.norm_k.weight", (C,), 0.1, 1.0
+        if cfg.cross_attn_norm:
+            yield p + "norm3.weight", (C,), 0.1, 1.0
+            yield p + "norm3.bias", (C,), w, 0.0
+        names = ("q", "k", "v", "o") + (("k_img", "v_img") if cfg.model_type == "i2v" else ())
+        for name in names:
+            yield p + f"cross_attn.{name}.weight", (C, C), w, 0.0
+            yield p + f"cross_attn.{name}.bias", (C,), w, 0.0
+        yield p + "cross_attn.norm_q.weight", (C,), 0.1, 1.0
+        yield p + "cross_attn.norm_k.weight", (C,), 0.1, 1.0
+        if cfg.model_type == "i2v":
+            yield p + "cross_attn.norm_k_img.weight", (C,), 0.1, 1.0
+        yield p + "ffn.0.weight", (F, C), w, 0.0
+        yield p + "ffn.0.bias", (F,), w, 0.0
+        yield p + "ffn.2.weight", (C, F), w, 0.0
+        yield p + "ffn.2.bias", (C,), w, 0.0
+        if cfg.use_spatial_guidance:
+            for s in ("spatial_guidance_self", "spatial_guidance_ffn"):
+                yield p + f"{s}.spatial_guide.1.weight", (2 * C, cfg.guidance_dim), w, 0.0
+                yield p + f"{s}.spatial_guide.1.bias", (2 * C,), w, 0.0
+                yield p + f"{s}.gate", (C,), 0.5, 0.0
+    yield "head.head.weight", (cfg.out_dim * pt * ph * pw, C), w, 0.0
+    yield "head.head.bias", (cfg.out_dim * pt * ph * pw,), w, 0.0
+    yield "head.modulation", (1, 2, C), C ** -0.5, 0.0
+    if cfg.model_type == "i2v":
+        D = cfg.clip_dim
+        yield "img_emb.proj.0.weight", (D,), 0.1, 1.0
+        yield "img_emb.proj.0.bias", (D,), w, 0.0
+        yield "img_emb.proj.1.weight", (D, D), w, 0.0
+        yield "img_emb.proj.1.bias", (D,), w, 0.0
+        yield "img_emb.proj.3.weight", (C, D), w, 0.0
+        yield "img_emb.proj.3.bias", (C,), w, 0.0
+        yield "img_emb.proj.4.weight", (C,), 0.1, 1.0
+        yield "img_emb.proj.4.bias", (C,), w, 0.0
+    if cfg.add_ref_conv:
+        yield "ref_conv.weight", (C, cfg.in_dim_ref_conv, ph, pw), 0.05, 0.0
+        yield "ref_conv.bias", (C,), w, 0.0
+
+
+def dit_state_dict(cfg: DiTConfig, seed: int = 0, device="cpu", dtype=torch.bfloat16,
+                   prefix_filter: str | None = None) -> Dict[str, torch.Tensor]:
+    """Synthetic state dict (bf16-valued) for the reference DiT layout."""
+    out = {}
+    for key, shape, std, mean in dit_param_specs(cfg):
+        if prefix_filter is not None and not key.startswith(prefix_filter):
+            continue
+        out[key] = _randn(seed, key, shape, std, device, dtype, mean)
+    return out
+
+
+def block_state_dict(cfg: DiTConfig, layer: int = 0, seed: int = 0, device="cpu",
+                     dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """State dict of one WanAttentionBlock with the ``blocks.N.`` prefix stripped."""
+    p = f"blocks.{layer}."
+    sd = dit_state_dict(cfg, seed, device, dtype, prefix_filter=p)
+    return {k[len(p):]: v for k, v in sd.items()}
+
+
+def dit_inputs(cfg: DiTConfig, grid: Tuple[int, int, int], batch: int = 1, seed: int = 0,
+               device="cpu", dtype=torch.bfloat16, text_tokens=(7, 11), with_ref: bool = True):
+    """Synthetic forward inputs with the reference call-surface layouts (t4d:1046-1060).
+
+    `grid` is the token grid (F, H, W) *including* the reference frame when `with_ref`.
+    Returns dict(x, y, t, context, clip_fea, full_ref, seq_len)."""
+    f, h, w = grid
+    lat_t = (f - 1 if with_ref else f) * cfg.patch_size[0]
+    lh, lw = h * cfg.patch_size[1], w * cfg.patch_size[2]
+    x = _randn(seed, "in.x", (batch, cfg.out_dim, lat_t, lh, lw), 1.0, device, dtype)
+    y = _randn(seed, "in.y", (batch, cfg.in_dim - cfg.out_dim, lat_t, lh, lw), 1.0, device, dtype)
+    context = [
+        _randn(seed, f"in.ctx{i}", (text_tokens[i % len(text_tokens)], cfg.text_dim), 1.0,
+               device, dtype) for i in range(batch)
+    ]
+    clip_fea = _randn(seed, "in.clip", (batch, cfg.clip_tokens, cfg.clip_dim), 1.0, device, dtype)
+    full_ref = _randn(seed, "in.ref", (batch, cfg.in_dim_ref_conv, lh, lw), 1.0, device, dtype) \
+        if with_ref else None
+    t = torch.full((batch,), 500.0, device=device)
+    seq_len = lat_t // cfg.patch_size[0] * h * w
+    return dict(x=x, y=y, t=t, context=context, clip_fea=clip_fea, full_ref=full_ref,
+                seq_len=seq_len)

@@ -1,0 +1,21 @@
+"""CPU oracle for the MoRe4D 4D-STraG hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``more4d_b200/`` may import this package.
+Allowed importers: ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` — and there only as the checker / the CPU
+baseline, never as the thing shipped.
+
+Contents
+--------
+``ref_import``  in-place importer for the real reference modules under ``/root/reference``
+                (authoring container only; the GPU box has no reference tree).  Used by
+                ``tests/golden/make_golden.py`` to generate the committed golden vectors and
+                by the CPU tests (when the tree is present) to cross-check the restatement.
+``dit_oracle``  torch-fp32 restatement of the Wan2.1-DiT forward (WanTransformer4DModel).
+``vae_oracle``  torch-fp32 restatement of the causal Wan VAE + trajectory adaptors.
+
+Parity pinning: the reference ships NO tests, golden vectors or fixtures,
+so parity is "unpinned by the reference's own tests".  The restatement is instead pinned
+against outputs of the *reference itself*, run in the authoring container through
+``ref_import`` and committed under ``tests/golden/`` with the generating script.
+"""

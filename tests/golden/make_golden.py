@@ -1,0 +1,128 @@
+"""Generate the committed golden vectors by running the REAL reference modules.
+
+Run in the authoring container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the reference in place through oracle/ref_import.py (stubs for the missing
+MoRe4D.dist and diffusers — SURVEY.md Appendix A), loads the synthetic state dicts of
+more4d_b200.synth (bf16-valued, upcast to fp32 = oracle mode A), runs the reference's own
+forward on CPU through its SDPA attention branch, and stores the outputs as safetensors.
+Weights and inputs are regenerated from seeds at test time; each file also stores input /
+weight checksums so RNG drift is detected rather than silently mis-compared.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import torch
+from safetensors.torch import save_file
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from more4d_b200 import synth                      # noqa: E402
+from more4d_b200.config import DiTConfig, WAN_1_3B, WAN_TINY   # noqa: E402
+from oracle import ref_import                      # noqa: E402
+from oracle.dit_oracle import time_embed           # noqa: E402  (only to build e0 from the seeded MLP)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_grad_enabled(False)
+
+
+def checksum(t: torch.Tensor) -> torch.Tensor:
+    t = t.double()
+    return torch.stack([t.sum(), t.abs().sum(), (t * t).sum()]).float()
+
+
+def f32(sd):
+    return {k: v.float() for k, v in sd.items()}
+
+
+def block_case(t4d, name, cfg: DiTConfig, grid, seq_len, seed, guidance=False):
+    C = cfg.dim
+    sd = synth.block_state_dict(cfg, 0, seed)
+    blk = t4d.WanAttentionBlock("i2v_cross_attn", C, cfg.ffn_dim, cfg.num_heads, (-1, -1), True,
+                                True, cfg.eps, use_spatial_guidance=cfg.use_spatial_guidance)
+    missing = blk.load_state_dict(f32(sd), strict=True)
+    x = synth._randn(seed, "blk.x", (1, seq_len, C), 1.0, "cpu", torch.bfloat16)
+    ctx = synth._randn(seed, "blk.ctx", (1, 257 + cfg.text_len, C), 1.0, "cpu", torch.bfloat16)
+    tsd = synth.dit_state_dict(cfg, seed, prefix_filter="time_")
+    _, e0 = time_embed(torch.tensor([500.0]), tsd, cfg.freq_dim, C)
+    d = cfg.head_dim
+    freqs = torch.cat([t4d.rope_params(1024, d - 4 * (d // 6)), t4d.rope_params(1024, 2 * (d // 6)),
+                       t4d.rope_params(1024, 2 * (d // 6))], dim=1)
+    n_tok = grid[0] * grid[1] * grid[2]
+    feats = None
+    if guidance:
+        feats = (synth._randn(seed, "blk.dino", (1, n_tok, cfg.guidance_dim), 1.0, "cpu", torch.float32),
+                 synth._randn(seed, "blk.cls", (1, 1, cfg.guidance_dim), 1.0, "cpu", torch.float32))
+    y = blk(x.float(), e0, torch.tensor([n_tok]), torch.tensor([list(grid)]), freqs, ctx.float(),
+            None, dtype=torch.float32, t=torch.tensor([500.0]), dino_features=feats)
+    out = {"y": y.contiguous(), "x_sum": checksum(x), "ctx_sum": checksum(ctx), "e0": e0.contiguous(),
+           "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))}
+    save_file(out, os.path.join(OUT, name + ".safetensors"))
+    print(name, tuple(y.shape), float(y.abs().mean()))
+
+
+def ops_case(t4d):
+    """Leaf ops: rope_apply, WanRMSNorm, attention (SDPA branch)."""
+    seed = 3
+    B, N, D = 2, 2, 128
+    grid = (2, 3, 4)
+    L = 30                                           # 24 rope'd tokens + 6 pass-through
+    q = synth._randn(seed, "op.q", (B, L, N, D), 1.0, "cpu", torch.float32)
+    k = synth._randn(seed, "op.k", (B, L, N, D), 1.0, "cpu", torch.float32)
+    v = synth._randn(seed, "op.v", (B, L, N, D), 1.0, "cpu", torch.float32)
+    freqs = torch.cat([t4d.rope_params(1024, D - 4 * (D // 6)), t4d.rope_params(1024, 2 * (D // 6)),
+                       t4d.rope_params(1024, 2 * (D // 6))], dim=1)
+    gs = torch.tensor([list(grid)] * B)
+    qr = t4d.rope_apply(q, gs, freqs)
+    nrm = t4d.WanRMSNorm(N * D, eps=1e-6)
+    w = synth._randn(seed, "op.w", (N * D,), 0.1, "cpu", torch.float32, mean=1.0)
+    nrm.weight.data.copy_(w)
+    qn = nrm(q.flatten(2))
+    att = t4d.attention(q, k, v, k_lens=torch.tensor([L, L]))
+    sin = t4d.sinusoidal_embedding_1d(256, torch.tensor([500.0, 999.0, 0.0]))
+    save_file({"rope": qr.contiguous(), "rms": qn.contiguous(), "attn": att.contiguous(),
+               "sinus": sin.float().contiguous(), "q_sum": checksum(q)},
+              os.path.join(OUT, "dit_ops.safetensors"))
+    print("dit_ops", tuple(att.shape))
+
+
+def model_case(t4d, name, cfg: DiTConfig, grid, batch, seed):
+    sd = synth.dit_state_dict(cfg, seed)
+    m = t4d.WanTransformer4DModel(
+        model_type="i2v", in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim,
+        num_heads=cfg.num_heads, num_layers=cfg.num_layers, text_dim=cfg.text_dim,
+        text_len=cfg.text_len, add_ref_conv=True, use_dino_guidance=False,
+        use_omnimae_guidance=False)
+    m.load_state_dict(f32(sd), strict=True)
+    m.eval()
+    inp = synth.dit_inputs(cfg, grid, batch, seed)
+    y = m(x=inp["x"].float(), t=inp["t"], context=[c.float() for c in inp["context"]],
+          seq_len=inp["seq_len"], clip_fea=inp["clip_fea"].float(), y=inp["y"].float(),
+          full_ref=inp["full_ref"].float())
+    save_file({"y": y.contiguous(), "x_sum": checksum(inp["x"]),
+               "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))},
+              os.path.join(OUT, name + ".safetensors"))
+    print(name, tuple(y.shape), float(y.abs().mean()))
+
+
+def main():
+    t4d, _vae, _traj = ref_import.load()
+    ops_case(t4d)
+    tiny = WAN_TINY
+    block_case(t4d, "block_tiny", tiny, (2, 3, 4), 30, seed=1)
+    block_case(t4d, "block_tiny_mpm", tiny.with_(use_spatial_guidance=True), (2, 3, 4), 30, seed=2,
+               guidance=True)
+    # BASELINE.json configs[0]: single DiT block, [1, 2x9x16, 1536], t=500
+    block_case(t4d, "block_config1", WAN_1_3B.with_(num_layers=1), (2, 9, 16), 288, seed=0)
+    model_case(t4d, "dit_tiny", tiny, (3, 4, 6), 2, seed=4)
+
+
+if __name__ == "__main__":
+    main()
