@@ -1,0 +1,139 @@
+/* more4d_b200 — C ABI of libmore4d_sm100.so
+ *
+ * Drop-in boundary for the 4D-STraG denoising hot path of Zhangyr2022/MoRe4D on NVIDIA B200
+ * (sm_100a).  The reference has no FFI of its own: its hot path is Python calling torch /
+ * flash-attn library kernels.  Each entry point below replaces the library
+ * call(s) cited next to it; the Python shim in more4d_b200/ binds them with ctypes and
+ * mirrors the reference's call surface.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all tensor pointers are DEVICE pointers
+ *   - "bf16" = __nv_bfloat16 storage; strides are in ELEMENTS unless stated otherwise
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream)
+ *   - the caller owns every buffer; the library never allocates or keeps device pointers
+ *   - return 0 on success, a negative M4D_ERR_* otherwise (m4d_error_string decodes it);
+ *     launches are asynchronous, so device-side faults surface at the caller's next sync
+ *   - no CPU fallback: without an sm_100 device every compute entry point fails
+ */
+#ifndef MORE4D_B200_H
+#define MORE4D_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  M4D_OK = 0,
+  M4D_ERR_BAD_SHAPE = -1,
+  M4D_ERR_UNSUPPORTED = -2,
+  M4D_ERR_ALIGN = -3,
+  M4D_ERR_WORKSPACE = -4,
+  M4D_ERR_CUDA = -5,
+  M4D_ERR_NO_DEVICE = -6
+};
+
+/* GEMM epilogues.  Every one first rounds (acc + bias) to bf16, which is what the reference's
+ * autocast nn.Linear hands to the next op. */
+enum {
+  M4D_EPI_BF16 = 0,              /* out bf16 = acc + bias                                   */
+  M4D_EPI_GELU_TANH = 1,         /* out bf16 = GELU_tanh(.)   ffn.1, text_embedding.1       */
+  M4D_EPI_GELU_ERF = 2,          /* out bf16 = GELU_erf(.)    img_emb.proj.2                */
+  M4D_EPI_F32 = 3,               /* out fp32 = (.)            patch/ref embedding -> x      */
+  M4D_EPI_GATE_RESIDUAL_F32 = 4, /* out fp32 = residual + (.) * gate[row / rows_per_batch]  */
+  M4D_EPI_COUNT = 5
+};
+
+int m4d_version(void);
+const char* m4d_error_string(int code);
+/* M4D_OK iff the current device is compute capability 10.x. */
+int m4d_device_check(void);
+/* Debug-only kernel variants (bit 0: swap V descriptor LBO/SBO, bit 1: swap P pack order). */
+void m4d_set_debug_flags(int flags);
+
+/* out[M,N] = epilogue(a[M,K] . w[N,K]^T + bias[N]) — tcgen05/TMEM GEMM, TMA-fed.
+ * Replaces nn.Linear (cuBLAS) at wan_transformer4d.py:446-448,465 (self-attn q/k/v/o),
+ * :481-483,527-531,553 (cross-attn), :620-622 (FFN), :720 (head), :900-902 (text embedding),
+ * :729-733 (MLPProj) and, fed by m4d_patchify, the patch/ref convolutions :1073,1087.
+ * a, w: bf16 row-major with row strides lda, ldw (multiples of 8); bias: bf16 or NULL.
+ * M4D_EPI_GATE_RESIDUAL_F32 fuses `x = x + y * e[k]` (:669,:684) / `x = x + y` (:674):
+ * residual fp32 [M, ldr] (may alias out), gate fp32 [*, N] with batch stride
+ * gate_batch_stride, or NULL for gate = 1. */
+int m4d_gemm_bf16(const void* a, long long lda, const void* w, long long ldw, const void* bias,
+                  void* out, long long ldo, int M, int N, int K, int epilogue,
+                  const float* residual, long long ldr, const float* gate,
+                  long long gate_batch_stride, int rows_per_batch, void* stream);
+
+/* out[b,l,h,:] = softmax(q k^T * scale) v, non-causal, head_dim 128, bf16 "NHD" layout
+ * [B, L, heads, 128] with explicit batch / token strides (so q,k,v may be views).
+ * Replaces attention()/flash_attention() wan_transformer4d.py:66-236 (flash_attn_varlen_func
+ * :138-169, SDPA :232).  k_lens (device int32 [B] or NULL) trims keys per sample like the
+ * varlen path.  softmax_scale <= 0 selects 1/sqrt(128).  accumulate != 0 adds the result into
+ * `out` in bf16 (the summed image+text cross-attention, :552). */
+int m4d_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int Lq,
+                      int Lk, int heads, int head_dim, long long q_stride_b, long long q_stride_l,
+                      long long kv_stride_b, long long kv_stride_l, long long out_stride_b,
+                      long long out_stride_l, const int* k_lens, float softmax_scale,
+                      int accumulate, void* stream);
+
+/* out = LayerNorm(x) [* weight + bias] [* (1 + scale[b]) + shift[b]], one pass.
+ * Replaces F.layer_norm + modulation at wan_transformer4d.py:662,677 (norm1/norm2 + AdaLN),
+ * :674 (norm3, affine), :720 (head), :729,733 (MLPProj).  x fp32 or bf16 [rows, C]; weight,
+ * bias bf16 [C] or NULL; shift, scale fp32 [*, C] (batch stride mod_batch_stride) or NULL;
+ * out bf16 or fp32.  Optional Motion-Perception-Module injection (:757-783): sg bf16
+ * [B, sg_rows, 2C] = Linear(SiLU(features)) as (scale | shift), sg_gate bf16 [C]. */
+int m4d_layernorm_modulate(const void* x, int x_is_bf16, const void* weight, const void* bias,
+                           const float* shift, const float* scale, long long mod_batch_stride,
+                           long long rows, int rows_per_batch, int C, float eps, void* out,
+                           int out_is_f32, const void* sg, long long sg_batch_stride, int sg_rows,
+                           const void* sg_gate, void* stream);
+
+/* In place on bf16 x [B, L, heads*head_dim] (row stride row_stride): WanRMSNorm over the full
+ * channel dim (wan_transformer4d.py:378-394; weight NULL skips it) then 3-axis RoPE on
+ * adjacent pairs (:340-375; rope_cos NULL skips it).  rope_cos/rope_sin: fp32 [1024, 64]
+ * roundings of the reference's float64 `freqs` table; grid_fhw: device int32 [B, 3]. */
+int m4d_rmsnorm_rope(void* x, long long row_stride, const void* weight, const float* rope_cos,
+                     const float* rope_sin, const int* grid_fhw, int B, int L, int heads,
+                     int head_dim, float eps, void* stream);
+
+/* y[M,N] fp32 = [SiLU](x[M,K] fp32) . w[N,K]^T(bf16) + bias, optional SiLU on y; M <= 8.
+ * The time-embedding MLPs, which the reference runs in fp32 (wan_transformer4d.py:1160-1171). */
+int m4d_small_linear_f32(const float* x, const void* w, const void* bias, float* y, int M, int N,
+                         int K, int silu_in, int silu_out, void* stream);
+
+/* sinusoidal_embedding_1d (wan_transformer4d.py:239-249): out fp32 [B, dim] = cos | sin,
+ * evaluated in float64. */
+int m4d_timestep_embedding(const float* t, int B, int dim, float* out, void* stream);
+
+/* out[b, i] = a[i] + e[b, i % m], i < n, m | n — `modulation + e0` (wan_transformer4d.py:659,
+ * m == n) and the head's `modulation + e.unsqueeze(1)` (:717, n == 2m). */
+int m4d_add_bcast_f32(const void* a_bf16, const float* e, float* out, int B, long long n,
+                      long long m, void* stream);
+
+/* im2col of the (1,2,2) patch convolution over cat(x, y) channels
+ * (wan_transformer4d.py:1069-1073): out bf16 [B, T*(H/2)*(W/2), (Cx+Cy)*4]. */
+int m4d_patchify(const void* x, const void* y, int B, int Cx, int Cy, int T, int H, int W,
+                 void* out, void* stream);
+
+/* unpatchify (wan_transformer4d.py:1343-1366) after dropping `skip_tokens` reference tokens
+ * (:1323-1326): tokens bf16 [B, *, 4*Cout] -> out bf16 [B, Cout, T, H, W]. */
+int m4d_unpatchify(const void* tokens, long long tok_batch_stride, int skip_tokens, int B,
+                   int Cout, int T, int H, int W, void* out, void* stream);
+
+/* dst[b, dst_row0 + r, :] (fp32) = src[b*rows + r, :] (bf16): token rows into the fp32
+ * residual stream (wan_transformer4d.py:1099-1106 concat/pad). */
+int m4d_widen_rows(const void* src_bf16, float* dst, int B, int rows, int C,
+                   long long dst_batch_stride, int dst_row0, void* stream);
+
+/* CFG combine + flow-matching Euler step on bf16 latents
+ * (pipeline_wan_fun_control.py:820-825). */
+int m4d_cfg_euler_step(const void* uncond, const void* text, void* latents, float guidance,
+                       float dt, long long n, void* stream);
+
+/* out bf16 = SiLU(x fp32), n % 4 == 0 — input of the Motion-Perception-Module projection
+ * (wan_transformer4d.py:746-748,781). */
+int m4d_silu_bf16(const float* x, void* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORE4D_B200_H */

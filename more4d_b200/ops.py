@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI: validate, pass data_ptr()s + strides, launch on the
+current torch stream.  No arithmetic happens in Python/torch here; torch only owns memory."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BF16, EPI_F32, EPI_GATE_RESIDUAL_F32, EPI_GELU_ERF,  # noqa: F401
+                   EPI_GELU_TANH)
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"more4d_b200: `{name}` must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"more4d_b200: `{name}` must be {dtype}, got {t.dtype}")
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: int = EPI_BF16,
+           out: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+           gate: Optional[Tensor] = None, gate_batch_stride: int = 0,
+           rows_per_batch: int = 0) -> Tensor:
+    """out = epilogue(x @ weight.T + bias).  x: [..., K] bf16 (last dim contiguous, uniform row
+    stride); weight: [N, K] bf16 (an nn.Linear weight, consumed in place)."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    _req(weight, BF16, "weight")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.dim() != 2:
+        weight = weight.reshape(N, -1)
+    if weight.shape[1] != K:
+        raise ValueError(f"more4d_b200.linear: K mismatch {weight.shape[1]} vs {K}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    if weight.stride(-1) != 1:
+        raise ValueError("more4d_b200.linear: weight rows must be contiguous")
+    M = x2.shape[0]
+    f32_out = epilogue in (EPI_F32, EPI_GATE_RESIDUAL_F32)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32 if f32_out else BF16)
+    _req(out, torch.float32 if f32_out else BF16, "out")
+    out2 = out.reshape(-1, N) if out.is_contiguous() else out
+    if out2.dim() != 2 or out2.shape[0] != M or out2.stride(-1) != 1:
+        raise ValueError("more4d_b200.linear: `out` must be viewable as [M, N] with unit col stride")
+    res2 = None
+    if epilogue == EPI_GATE_RESIDUAL_F32:
+        if residual is None:
+            raise ValueError("more4d_b200.linear: residual required")
+        _req(residual, torch.float32, "residual")
+        res2 = residual.reshape(-1, N)
+        if gate is not None:
+            _req(gate, torch.float32, "gate")
+    if bias is not None:
+        _req(bias, BF16, "bias")
+    rc = _lib.lib().m4d_gemm_bf16(
+        x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
+        out2.data_ptr(), out2.stride(0), M, N, K, epilogue,
+        _ptr(res2), 0 if res2 is None else res2.stride(0), _ptr(gate), gate_batch_stride,
+        rows_per_batch, _stream())
+    _lib.check(rc, "m4d_gemm_bf16")
+    return out
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, k_lens: Optional[Tensor] = None,
+              softmax_scale: Optional[float] = None, out: Optional[Tensor] = None,
+              accumulate: bool = False) -> Tensor:
+    """softmax(q k^T * scale) v.  q: [B, Lq, N, 128], k/v: [B, Lk, N, 128] bf16; the head and
+    channel dims must be contiguous, batch/token strides are free.  k_lens: int32 CUDA [B]."""
+    _lib.require_device()
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, BF16, n)
+        if t.dim() != 4 or t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+            raise ValueError(f"more4d_b200.attention: `{n}` must be [B, L, N, D] with contiguous (N, D)")
+    B, Lq, N, D = q.shape
+    Lk = k.shape[1]
+    if k.shape != v.shape or k.shape[0] != B or k.shape[2] != N or k.shape[3] != D:
+        raise ValueError("more4d_b200.attention: q/k/v shape mismatch")
+    if k.stride() != v.stride():
+        v = v.contiguous()
+        k = k.contiguous()
+    if out is None:
+        out = torch.empty(B, Lq, N, D, device=q.device, dtype=BF16)
+    _req(out, BF16, "out")
+    if k_lens is not None:
+        _req(k_lens, torch.int32, "k_lens")
+    rc = _lib.lib().m4d_attention_fwd(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Lq, Lk, N, D,
+        q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
+        _ptr(k_lens), float(softmax_scale) if softmax_scale else 0.0, int(accumulate), _stream())
+    _lib.check(rc, "m4d_attention_fwd")
+    return out
+
+
+def layernorm_modulate(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+                       shift: Optional[Tensor] = None, scale: Optional[Tensor] = None,
+                       mod_batch_stride: int = 0, rows_per_batch: Optional[int] = None,
+                       eps: float = 1e-6, out_dtype=BF16, guidance: Optional[Tensor] = None,
+                       guidance_gate: Optional[Tensor] = None) -> Tensor:
+    """LayerNorm over the last dim (+affine) (+AdaLN `*(1+scale)+shift`) in one pass.
+    shift/scale: fp32 views whose element [b, :] sits at data_ptr + b*mod_batch_stride."""
+    _lib.require_device()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if x.dtype not in (torch.float32, BF16):
+        raise TypeError("more4d_b200.layernorm_modulate: x must be fp32 or bf16")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    sg_rows, sg_stride = 0, 0
+    if guidance is not None:
+        _req(guidance, BF16, "guidance")
+        guidance = guidance.contiguous()
+        sg_rows = guidance.shape[1]
+        sg_stride = guidance.stride(0)
+    rc = _lib.lib().m4d_layernorm_modulate(
+        x.data_ptr(), int(x.dtype == BF16), _ptr(weight), _ptr(bias), _ptr(shift), _ptr(scale),
+        mod_batch_stride, rows, rows_per_batch or rows, C, eps, out.data_ptr(),
+        int(out_dtype == torch.float32), _ptr(guidance), sg_stride, sg_rows, _ptr(guidance_gate),
+        _stream())
+    _lib.check(rc, "m4d_layernorm_modulate")
+    return out
+
+
+def rmsnorm_rope_(x: Tensor, weight: Optional[Tensor], heads: int, eps: float = 1e-6,
+                  rope_cos: Optional[Tensor] = None, rope_sin: Optional[Tensor] = None,
+                  grid_fhw: Optional[Tensor] = None) -> Tensor:
+    """In place: WanRMSNorm over all channels, then 3-axis RoPE.  x: [B, L, heads*D] bf16."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    B, L, C = x.shape
+    if x.stride(2) != 1 or x.stride(0) != L * x.stride(1):
+        raise ValueError("more4d_b200.rmsnorm_rope_: x rows must be uniformly strided")
+    if rope_cos is not None:
+        _req(rope_cos, torch.float32, "rope_cos")
+        _req(grid_fhw, torch.int32, "grid_fhw")
+    rc = _lib.lib().m4d_rmsnorm_rope(x.data_ptr(), x.stride(1), _ptr(weight), _ptr(rope_cos),
+                                     _ptr(rope_sin), _ptr(grid_fhw), B, L, heads, C // heads, eps,
+                                     _stream())
+    _lib.check(rc, "m4d_rmsnorm_rope")
+    return x
+
+
+def small_linear_f32(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu_in: bool = False,
+                     silu_out: bool = False) -> Tensor:
+    _lib.require_device()
+    _req(x, torch.float32, "x")
+    _req(weight, BF16, "weight")
+    x = x.contiguous()
+    M, K = x.shape
+    N = weight.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().m4d_small_linear_f32(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(),
+                                         M, N, K, int(silu_in), int(silu_out), _stream())
+    _lib.check(rc, "m4d_small_linear_f32")
+    return y
+
+
+def timestep_embedding(t: Tensor, dim: int) -> Tensor:
+    _lib.require_device()
+    t = t.to(device="cuda", dtype=torch.float32).contiguous()
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    rc = _lib.lib().m4d_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream())
+    _lib.check(rc, "m4d_timestep_embedding")
+    return out
+
+
+def add_bcast(a_bf16: Tensor, e: Tensor) -> Tensor:
+    """out[b, i] = a[i] + e[b, i % m]  (a: bf16 with n = r*m elements, e: fp32 [B, m]) -> fp32
+    [B, n]."""
+    _lib.require_device()
+    _req(a_bf16, BF16, "a")
+    _req(e, torch.float32, "e")
+    e = e.contiguous()
+    B = e.shape[0]
+    m = e.numel() // B
+    n = a_bf16.numel()
+    if n % m != 0:
+        raise ValueError("more4d_b200.add_bcast: size mismatch")
+    out = torch.empty(B, n, device=e.device, dtype=torch.float32)
+    rc = _lib.lib().m4d_add_bcast_f32(a_bf16.data_ptr(), e.data_ptr(), out.data_ptr(), B, n, m,
+                                      _stream())
+    _lib.check(rc, "m4d_add_bcast_f32")
+    return out
+
+
+def patchify(x: Tensor, y: Optional[Tensor] = None) -> Tensor:
+    """[B, Cx, T, H, W] (+ [B, Cy, T, H, W]) -> im2col rows [B, T*(H/2)*(W/2), (Cx+Cy)*4]."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    x = x.contiguous()
+    B, Cx, T, H, W = x.shape
+    Cy = 0
+    if y is not None:
+        _req(y, BF16, "y")
+        y = y.contiguous()
+        Cy = y.shape[1]
+    out = torch.empty(B, T * (H // 2) * (W // 2), (Cx + Cy) * 4, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_patchify(x.data_ptr(), _ptr(y), B, Cx, Cy, T, H, W, out.data_ptr(), _stream())
+    _lib.check(rc, "m4d_patchify")
+    return out
+
+
+def unpatchify(tokens: Tensor, skip_tokens: int, cout: int, T: int, H: int, W: int) -> Tensor:
+    """tokens [B, L, 4*cout] bf16 -> [B, cout, T, H, W] (H, W = latent size)."""
+    _lib.require_device()
+    _req(tokens, BF16, "tokens")
+    tokens = tokens.contiguous()
+    B = tokens.shape[0]
+    out = torch.empty(B, cout, T, H, W, device=tokens.device, dtype=BF16)
+    rc = _lib.lib().m4d_unpatchify(tokens.data_ptr(), tokens.stride(0), skip_tokens, B, cout, T, H,
+                                   W, out.data_ptr(), _stream())
+    _lib.check(rc, "m4d_unpatchify")
+    return out
+
+
+def widen_rows(src: Tensor, dst: Tensor, dst_row0: int) -> None:
+    """dst[b, dst_row0:dst_row0+rows, :] (fp32) = src[b, :, :] (bf16)."""
+    _lib.require_device()
+    _req(src, BF16, "src")
+    _req(dst, torch.float32, "dst")
+    src = src.contiguous()
+    B, rows, C = src.shape
+    rc = _lib.lib().m4d_widen_rows(src.data_ptr(), dst.data_ptr(), B, rows, C, dst.stride(0),
+                                   dst_row0, _stream())
+    _lib.check(rc, "m4d_widen_rows")
+
+
+def cfg_euler_step_(latents: Tensor, uncond: Tensor, text: Tensor, guidance: float, dt: float) -> Tensor:
+    _lib.require_device()
+    for n, t in (("latents", latents), ("uncond", uncond), ("text", text)):
+        _req(t, BF16, n)
+        if not t.is_contiguous():
+            raise ValueError(f"more4d_b200.cfg_euler_step_: `{n}` must be contiguous")
+    rc = _lib.lib().m4d_cfg_euler_step(uncond.data_ptr(), text.data_ptr(), latents.data_ptr(),
+                                       guidance, dt, latents.numel(), _stream())
+    _lib.check(rc, "m4d_cfg_euler_step")
+    return latents
+
+
+def silu_bf16(x: Tensor) -> Tensor:
+    """bf16(SiLU(x)) for fp32 x."""
+    _lib.require_device()
+    _req(x, torch.float32, "x")
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "m4d_silu_bf16")
+    return out

@@ -1,0 +1,110 @@
+"""First-contact diagnostics for the tcgen05 kernels on a real B200 (development tool).
+Usage: python tools/gpu_probe.py {gemm|attn|rows}"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from more4d_b200 import _lib, ops           # noqa: E402
+from oracle import dit_oracle as O          # noqa: E402
+
+BF16 = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(BF16)
+
+
+def gemm():
+    for (M, N, K) in [(128, 256, 64), (128, 256, 256), (300, 320, 192), (4096, 5120, 5120)]:
+        a, w = rnd((M, K), 1), rnd((N, K), 2, 0.05)
+        out = ops.linear(a.cuda(), w.cuda(), None)
+        torch.cuda.synchronize()
+        ref = (a.cuda().float() @ w.cuda().float().t())
+        e = rel(out.float(), ref)
+        print(f"gemm {M}x{N}x{K}: rel={e:.3e}", flush=True)
+        if e > 1e-2 and M <= 300:
+            d = (out.float() - ref).abs().cpu()
+            print("  err by 32-col block:", [round(float(d[:, c:c + 32].mean()), 3) for c in range(0, N, 32)])
+            print("  err by 32-row block:", [round(float(d[r:r + 32].mean()), 3) for r in range(0, M, 32)])
+            # K-slice probe: which k-columns contribute correctly?
+            for k0 in range(0, K, 16):
+                a2 = torch.zeros_like(a); a2[:, k0:k0 + 16] = a[:, k0:k0 + 16]
+                o2 = ops.linear(a2.cuda(), w.cuda(), None).float()
+                r2 = a2.cuda().float() @ w.cuda().float().t()
+                print(f"  k-slice {k0}: rel={rel(o2, r2):.3e}")
+    # timing of the big one
+    M, N, K = 8192, 5120, 5120
+    a, w = rnd((M, K), 1).cuda(), rnd((N, K), 2, 0.05).cuda()
+    out = torch.empty(M, N, device="cuda", dtype=BF16)
+    for _ in range(3):
+        ops.linear(a, w, None, out=out)
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    for _ in range(10):
+        ops.linear(a, w, None, out=out)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f"gemm {M}x{N}x{K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    s.record()
+    for _ in range(10):
+        torch.matmul(a, w.t(), out=out)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f"cublas same shape: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
+def attn():
+    ar = O.Arith(True)
+    for flags in (0, 1, 2, 3):
+        _lib.lib().m4d_set_debug_flags(flags)
+        for (B, Lq, Lk, N) in [(1, 128, 128, 1), (1, 256, 384, 2), (2, 300, 257, 2)]:
+            q, k, v = rnd((B, Lq, N, 128), 1), rnd((B, Lk, N, 128), 2), rnd((B, Lk, N, 128), 3)
+            out = ops.attention(q.cuda(), k.cuda(), v.cuda())
+            torch.cuda.synchronize()
+            ref = O.attention(q, k, v, None, ar)
+            print(f"attn flags={flags} B{B} Lq{Lq} Lk{Lk} N{N}: rel={rel(out.float().cpu(), ref):.3e} "
+                  f"finite={bool(torch.isfinite(out).all())}", flush=True)
+    _lib.lib().m4d_set_debug_flags(0)
+    # structured probes: V = one-hot rows => O[q] = P[q, :] picks; uniform P (q=0) => O = mean(V)
+    B, L, N = 1, 128, 1
+    q = torch.zeros(B, L, N, 128, dtype=BF16)
+    k = rnd((B, L, N, 128), 2)
+    v = rnd((B, L, N, 128), 3)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda()).float().cpu()
+    print("uniform-P probe: rel vs mean(V) =", rel(out[0, :, 0], v[0, :, 0].float().mean(0, keepdim=True).expand(L, 128)))
+    # timing
+    for (B, L, N) in [(1, 8192, 12), (1, 21840, 12), (2, 50400, 40)]:
+        q, k, v = (torch.randn(B, L, N, 128, device="cuda", dtype=BF16) for _ in range(3))
+        out = torch.empty_like(q)
+        ops.attention(q, k, v, out=out)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record()
+        ops.attention(q, k, v, out=out)
+        e.record(); torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        fl = 4.0 * B * N * L * L * 128
+        print(f"attn B{B} L{L} N{N}: {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+        if L <= 21840:
+            with torch.nn.attention.sdpa_kernel(torch.nn.attention.SDPBackend.FLASH_ATTENTION):
+                qq, kk, vv = (t.transpose(1, 2) for t in (q, k, v))
+                o2 = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv)
+                torch.cuda.synchronize()
+                s.record()
+                o2 = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv)
+                e.record(); torch.cuda.synchronize()
+                print(f"   torch SDPA(flash): {s.elapsed_time(e):.2f} ms  {fl/s.elapsed_time(e)/1e9:.1f} TFLOP/s;"
+                      f" rel vs ours {rel(out.float(), o2.transpose(1, 2).float()):.3e}", flush=True)
+
+
+if __name__ == "__main__":
+    torch.set_grad_enabled(False)
+    {"gemm": gemm, "attn": attn}[sys.argv[1]]()
