@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Benchmark of BASELINE.json's metric: 4D-STraG denoise-step latents/sec at 49x720x1280.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One *step* = one latent-step of the reference's denoising loop (pipeline_wan_fun_control.py:
+741-840): one DiT forward on the CFG-doubled batch + CFG combine + Euler update, on synthetic
+latents / conditioning and seeded random weights of the Wan2.1-14B-Control architecture
+(no checkpoints or datasets are reachable).  N > 1: one process per GPU (torchrun), every rank
+denoises its own sample (the batch axis of the north-star; weak scaling), no data-path
+collective inside a step, one NCCL all-gather of the final latents inside the timed region.
+
+JSON keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config preset, frames, height, width)
+    "720p-14b": ("WAN_14B", 49, 720, 1280),
+    "480p-14b": ("WAN_14B", 49, 480, 832),
+    "720p-1.3b": ("WAN_1_3B", 49, 720, 1280),
+    "480p-1.3b": ("WAN_1_3B", 49, 480, 832),
+    "tiny": ("WAN_TINY", 9, 64, 96),
+}
+METRIC = "4D-STraG denoise-step latents/sec @49x720p"
+UNIT = "latent-steps/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", 1424.9), p.get("bf16_tflops", 1679.0), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        busy = sorted(sm)[len(sm) // 4:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_arm(args, cfg, L, grid, rank, repeats=1, skip=0):
+    """`--impl reference` and the cpu_baseline leg: the oracle port of the block on host cores."""
+    import torch
+    from oracle import cpu_baseline
+    rows = args.cpu_sample_rows
+    times, threads = cpu_baseline.time_block_sample(cfg, L, rows, grid, seed=0, repeats=max(1, repeats))
+    times = times[skip:] if len(times) > skip else times
+    t_best = min(times)
+    value = cpu_baseline.latent_steps_per_s(t_best, L, rows, cfg.num_layers)
+    sample = (f"1 of {cfg.num_layers} blocks, {rows} of {L} query rows vs all {L} keys, 1 of 2 CFG "
+              f"branches, fp32 oracle port; extrapolated linearly to a full latent-step "
+              f"(x{L / rows:.1f} x{cfg.num_layers} x2); best of {len(times)}: {t_best:.2f} s")
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="720p-14b", choices=sorted(WORKLOADS))
+    ap.add_argument("--layers", type=int, default=0, help="debug only: truncate the block stack (number is then INVALID)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    from more4d_b200 import config as mcfg
+
+    preset, frames, height, width = WORKLOADS[args.workload]
+    cfg = getattr(mcfg, preset)
+    if args.layers:
+        cfg = cfg.with_(num_layers=args.layers)
+    grid = mcfg.token_grid(frames, height, width, cfg)
+    L = grid[0] * grid[1] * grid[2]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: Wan2.1-14B-Control dims (C{cfg.dim} F{cfg.ffn_dim} "
+                          f"{cfg.num_heads}h x{cfg.num_layers}L) {frames}x{height}x{width}, "
+                          f"L={L} tokens, CFG batch 2, 1 sample/GPU",
+              "parallelism": f"dp{world} (sample-sharded replicas, all-gather of final latents)",
+              "l2": "inputs (28 GB weights + GB-scale activations) exceed the 126 MB L2 every step",
+              "layers_override": args.layers or None}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_grad_enabled(False)
+        cb, times = cpu_reference_arm(args, cfg, L, grid, rank, repeats=args.warmup + args.steps,
+                                      skip=args.warmup)
+        t_mean = sum(times) / len(times)
+        from oracle import cpu_baseline
+        value = cpu_baseline.latent_steps_per_s(t_mean, L, args.cpu_sample_rows, cfg.num_layers)
+        cb["value"] = value
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import torch.distributed as dist
+    from more4d_b200 import ops, synth
+    from more4d_b200.dit import WanTransformer4DModel
+    from more4d_b200.pipeline import StraGDenoiser, synthetic_conditioning
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+
+    model = WanTransformer4DModel.from_config(cfg, device=dev)
+    synth.fill_module_(model, cfg, seed=0)
+    den = StraGDenoiser(model, guidance_scale=6.0, shift=5.0, num_inference_steps=50)
+    lat_t = (frames - 1) // 4 + 1
+    latent_shape = (1, 16, lat_t, height // 8, width // 8)
+    lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True)
+    lat = lat_host.to(dev)
+    cond = cond_host.to(dev)
+    gathered = [torch.empty_like(lat) for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, latents, first_step=0):
+        for s in range(steps):
+            den.step(latents, (first_step + s) % den.num_inference_steps, cond)
+
+    # warm-up (also JITs nothing: all kernels are prebuilt; this pages weights and warms clocks)
+    run(args.warmup, lat)
+    barrier()
+
+    # ---- device-resident timing ("value") with per-launch timing of the dominant kernel
+    sampler = ClockSampler(local_rank)
+    ops.start_kernel_timing()
+    l0 = ops.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    run(args.steps, lat, args.warmup)
+    if world > 1:
+        dist.all_gather(gathered, lat)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    timed = ops.stop_kernel_timing()
+    launches = ops.launches() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * args.steps / (ms_total / 1000.0)
+
+    # ---- end to end through the public API with HOST buffers (pinned H2D in, D2H out, every step)
+    h2d = lat_host.numel() * 2 + cond_host.nbytes()
+    d2h = lat_host.numel() * 2
+    barrier()
+    t0 = time.perf_counter()
+    cur = lat_host
+    for s in range(args.steps):
+        cur = den(cur, cond_host, steps=[(args.warmup + s) % den.num_inference_steps], device=dev)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    sust, burst, src = _peaks()
+    att = timed["attention"]
+    att_ms = [a.elapsed_time(b) for a, b, _ in att]
+    att_fl = att[0][2] if att else 0.0
+    avg_ms = sum(att_ms) / max(1, len(att_ms))
+    achieved = att_fl / (avg_ms / 1e3) / 1e12 if att else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "attention_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload)
+    roofline = {"kernel": "attn_fwd_d128_kernel (self-attention launches, Lq=Lk=L)", "bound": "tensor",
+                "achieved": achieved, "peak": sust, "unit": "TFLOP/s", "frac": achieved / sust,
+                "frac_of_burst_peak": achieved / burst, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
+                "launches_timed": len(att), "avg_launch_ms": avg_ms,
+                "share_of_step": sum(att_ms) / ms_total if ms_total else None,
+                "algorithmic_flops_per_launch": att_fl, "traffic": traffic}
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_reference_arm(args, cfg, L, grid, rank)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "dit_forwards_per_s": value * 2,
+            "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

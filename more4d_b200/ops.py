@@ -14,7 +14,28 @@ Tensor = torch.Tensor
 BF16 = torch.bfloat16
 
 
+class _Stats:
+    """Launch accounting for bench.py: every C-ABI compute call is exactly one kernel launch."""
+    launches = 0
+    timed = None          # None, or {"attention": [(start_evt, end_evt, flops), ...]}
+
+
+def launches() -> int:
+    return _Stats.launches
+
+
+def start_kernel_timing() -> None:
+    """Bracket every self-attention launch with CUDA events on the launching stream."""
+    _Stats.timed = {"attention": []}
+
+
+def stop_kernel_timing():
+    t, _Stats.timed = _Stats.timed, None
+    return t
+
+
 def _stream() -> int:
+    _Stats.launches += 1
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -98,11 +119,18 @@ def attention(q: Tensor, k: Tensor, v: Tensor, k_lens: Optional[Tensor] = None,
     _req(out, BF16, "out")
     if k_lens is not None:
         _req(k_lens, torch.int32, "k_lens")
+    timed = _Stats.timed is not None and Lq == Lk
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = _lib.lib().m4d_attention_fwd(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Lq, Lk, N, D,
         q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
         _ptr(k_lens), float(softmax_scale) if softmax_scale else 0.0, int(accumulate), _stream())
     _lib.check(rc, "m4d_attention_fwd")
+    if timed:
+        ev1.record()
+        _Stats.timed["attention"].append((ev0, ev1, 4.0 * B * N * Lq * Lk * D))
     return out
 
 

@@ -136,3 +136,17 @@ def dit_inputs(cfg: DiTConfig, grid: Tuple[int, int, int], batch: int = 1, seed:
     seq_len = lat_t // cfg.patch_size[0] * h * w
     return dict(x=x, y=y, t=t, context=context, clip_fea=clip_fea, full_ref=full_ref,
                 seq_len=seq_len)
+
+
+def fill_module_(module, cfg: DiTConfig, seed: int = 0) -> None:
+    """Fill a more4d_b200.dit.WanTransformer4DModel in place, one parameter at a time, on the
+    parameter's own device (no second copy of a 14B state dict)."""
+    sd = module.state_dict()
+    specs = {k: (shape, std, mean) for k, shape, std, mean in dit_param_specs(cfg)}
+    missing = set(sd) - set(specs)
+    if missing:
+        raise KeyError(f"no synthetic spec for parameters: {sorted(missing)[:5]} ...")
+    with torch.no_grad():
+        for key, p in sd.items():
+            shape, std, mean = specs[key]
+            p.copy_(_randn(seed, key, shape, std, p.device, p.dtype, mean))
