@@ -176,7 +176,8 @@ def main():
     den = StraGDenoiser(model, guidance_scale=6.0, shift=5.0, num_inference_steps=50)
     lat_t = (frames - 1) // 4 + 1
     latent_shape = (1, 16, lat_t, height // 8, width // 8)
-    lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True)
+    lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True,
+                                                 text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
     lat = lat_host.to(dev)
     cond = cond_host.to(dev)
     gathered = [torch.empty_like(lat) for _ in range(world)] if world > 1 else None

@@ -104,7 +104,8 @@ class StraGDenoiser:
 
 
 def synthetic_conditioning(latent_shape, seed: int = 0, device="cpu", pin: bool = False,
-                           prompt_tokens: int = 32, negative_tokens: int = 1):
+                           prompt_tokens: int = 32, negative_tokens: int = 1, text_dim: int = 4096,
+                           clip_dim: int = 1280):
     """Synthetic latents + conditioning of the BASELINE shapes."""
     g = torch.Generator().manual_seed(seed)
     _, c, T, h, w = latent_shape
@@ -117,5 +118,5 @@ def synthetic_conditioning(latent_shape, seed: int = 0, device="cpu", pin: bool 
 
     latents = rn(1, c, T, h, w)
     cond = StraGConditioning(rn(1, 16, T, h, w), rn(1, 16, T, h, w), rn(1, 16, h, w),
-                             rn(1, 257, 1280), rn(prompt_tokens, 4096), rn(negative_tokens, 4096))
+                             rn(1, 257, clip_dim), rn(prompt_tokens, text_dim), rn(negative_tokens, text_dim))
     return latents, cond
