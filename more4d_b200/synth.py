@@ -138,6 +138,33 @@ def dit_inputs(cfg: DiTConfig, grid: Tuple[int, int, int], batch: int = 1, seed:
                 seq_len=seq_len)
 
 
+def vae_state_dict(cfg=None, seed: int = 0, device="cpu", dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """Synthetic state dict of the reference AutoencoderKLWan (keys with the `model.` prefix)."""
+    from .vae_arch import WAN_VAE, vae_param_specs
+    return {k: _randn(seed, k, shape, std, device, dtype, mean)
+            for k, shape, std, mean in vae_param_specs(cfg or WAN_VAE)}
+
+
+def adaptor_state_dict(kind: str, seed: int = 0, device="cpu", dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """Synthetic state dict of VAEEncoderadaptor ("encoder") / VAEDecoderadaptor ("decoder")."""
+    from .vae_arch import adaptor_param_specs
+    return {k: _randn(seed, f"{kind}.{k}", shape, std, device, dtype, mean)
+            for k, shape, std, mean in adaptor_param_specs(kind)}
+
+
+def trajectory_video(frames: int, height: int, width: int, seed: int = 0, device="cpu",
+                     dtype=torch.bfloat16) -> torch.Tensor:
+    """Synthetic normalised xyz-displacement tensor [1, 3, F, H, W] shaped like the output of
+    scripts/inference/infer_vae.py:98-134 (smooth, frame 0 = 0, grows with t)."""
+    g = _gen(seed, "traj.video", "cpu")
+    low = torch.randn(1, 3, max(2, frames // 4 + 1), max(2, height // 16), max(2, width // 16),
+                      generator=g)
+    smooth = torch.nn.functional.interpolate(low, size=(frames, height, width), mode="trilinear",
+                                             align_corners=True)
+    ramp = torch.linspace(0, 1, frames).view(1, 1, frames, 1, 1)
+    return (smooth * ramp * 0.5).to(device=device, dtype=dtype)
+
+
 def fill_module_(module, cfg: DiTConfig, seed: int = 0) -> None:
     """Fill a more4d_b200.dit.WanTransformer4DModel in place, one parameter at a time, on the
     parameter's own device (no second copy of a 14B state dict)."""

@@ -112,8 +112,43 @@ def model_case(t4d, name, cfg: DiTConfig, grid, batch, seed):
     print(name, tuple(y.shape), float(y.abs().mean()))
 
 
+def vae_cases(vae_mod, traj_mod):
+    """Real AutoencoderKLWan (chunked encode/decode with the feature cache) and the two
+    trajectory adaptors on small clips: 13 frames = 1 + three 4-frame chunks on the encoder
+    side; 4 latent frames = 'Rep' chunk + three cached chunks on the decoder side."""
+    import contextlib, io
+    seed = 11
+    sd = synth.vae_state_dict(seed=seed)
+    m = vae_mod.AutoencoderKLWan()
+    m.load_state_dict(f32(sd), strict=True)
+    m.eval()
+    x = synth._randn(seed, "vae.x", (1, 3, 13, 32, 48), 0.5, "cpu", torch.bfloat16).float()
+    dist = m.encode(x)[0]
+    params = dist.parameters
+    z = synth._randn(seed, "vae.z", (1, 16, 4, 4, 6), 1.0, "cpu", torch.bfloat16).float()
+    rec = m.decode(z).sample
+    x1 = x[:, :, :1]
+    p1 = m.encode(x1)[0].parameters                       # single-frame clip (T = 1 edge case)
+    r1 = m.decode(z[:, :, :1]).sample
+    out = {"enc_params": params.contiguous(), "dec": rec.contiguous(), "enc_params_T1": p1.contiguous(),
+           "dec_T1": r1.contiguous(), "x_sum": checksum(x), "z_sum": checksum(z),
+           "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ea, da = traj_mod.VAEEncoderadaptor(), traj_mod.VAEDecoderadaptor()
+    esd, dsd = synth.adaptor_state_dict("encoder", seed), synth.adaptor_state_dict("decoder", seed)
+    ea.load_state_dict(f32(esd), strict=True)
+    da.load_state_dict(f32(dsd), strict=True)
+    tv = synth.trajectory_video(5, 32, 48, seed).float()
+    out["adaptor_enc"] = ea(tv).contiguous()
+    out["adaptor_dec"] = da(tv).contiguous()
+    out["tv_sum"] = checksum(tv)
+    save_file(out, os.path.join(OUT, "vae.safetensors"))
+    print("vae", tuple(params.shape), tuple(rec.shape), float(rec.abs().mean()))
+
+
 def main():
     t4d, _vae, _traj = ref_import.load()
+    vae_cases(_vae, _traj)
     ops_case(t4d)
     tiny = WAN_TINY
     block_case(t4d, "block_tiny", tiny, (2, 3, 4), 30, seed=1)
