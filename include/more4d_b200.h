@@ -40,7 +40,9 @@ enum {
   M4D_EPI_GELU_ERF = 2,          /* out bf16 = GELU_erf(.)    img_emb.proj.2                */
   M4D_EPI_F32 = 3,               /* out fp32 = (.)            patch/ref embedding -> x      */
   M4D_EPI_GATE_RESIDUAL_F32 = 4, /* out fp32 = residual + (.) * gate[row / rows_per_batch]  */
-  M4D_EPI_COUNT = 5
+  M4D_EPI_ADD_BF16 = 5,          /* out bf16 = (.) + residual_bf16   VAE AttentionBlock.proj */
+  M4D_EPI_F32_RAW = 6,           /* out fp32 = acc, no bias, no rounding (attention logits)  */
+  M4D_EPI_COUNT = 7
 };
 
 int m4d_version(void);
@@ -57,10 +59,10 @@ void m4d_set_debug_flags(int flags);
  * a, w: bf16 row-major with row strides lda, ldw (multiples of 8); bias: bf16 or NULL.
  * M4D_EPI_GATE_RESIDUAL_F32 fuses `x = x + y * e[k]` (:669,:684) / `x = x + y` (:674):
  * residual fp32 [M, ldr] (may alias out), gate fp32 [*, N] with batch stride
- * gate_batch_stride, or NULL for gate = 1. */
+ * gate_batch_stride, or NULL for gate = 1.  M4D_EPI_ADD_BF16 takes a bf16 residual. */
 int m4d_gemm_bf16(const void* a, long long lda, const void* w, long long ldw, const void* bias,
                   void* out, long long ldo, int M, int N, int K, int epilogue,
-                  const float* residual, long long ldr, const float* gate,
+                  const void* residual, long long ldr, const float* gate,
                   long long gate_batch_stride, int rows_per_batch, void* stream);
 
 /* out[b,l,h,:] = softmax(q k^T * scale) v, non-causal, head_dim 128, bf16 "NHD" layout
@@ -128,6 +130,63 @@ int m4d_widen_rows(const void* src_bf16, float* dst, int B, int rows, int C,
  * (pipeline_wan_fun_control.py:820-825). */
 int m4d_cfg_euler_step(const void* uncond, const void* text, void* latents, float guidance,
                        float dt, long long n, void* stream);
+
+/* ---- Motion-Sensitive VAE (wan_vae.py, trajectory_module.py), channels-last activations ---- */
+
+/* Causal 3-D / 2-D convolution as a tcgen05 implicit GEMM over a whole channels-last sequence
+ * x bf16 [T_in, H_in, W_in, Cin] (Cin % 32 == 0).  Replaces CausalConv3d.forward
+ * (wan_vae.py:32-40: cache cat + F.pad + cuDNN Conv3d), Resample's Conv2d's (:82-100) and the
+ * adaptors' Conv2d's (trajectory_module.py:73-87).  Padding (pt frames in FRONT, ph/pw on both
+ * spatial sides, right/bottom for strided convs) is TMA out-of-bounds zero fill.
+ * w_packed: bf16 [Cout_pad, kt*kh*kw*Cin], tap-major / channel-minor, rows >= Cout zero.
+ * Output element (t, h, w, n) goes to frame t*t_mul + t_off + n / n_split, channel n % n_split
+ * of a channels-last tensor with out_C channels (upsample3d's channel->frame interleave,
+ * wan_vae.py:138-141, is n_split = C); residual: same layout, added after bf16 rounding
+ * (ResidualBlock, :224).  out_mode 1 writes planar [Cout, T, H, W] instead, with act 1 =
+ * clamp(-1,1) (:827) or act 2 = sigmoid(y + skip) (trajectory_module.py:194). */
+int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin, const void* w_packed,
+                int Cout, int Cout_pad, const void* bias, int kt, int kh, int kw, int st, int sh,
+                int sw, int pt, int ph, int pw, int T_out, int H_out, int W_out, void* out,
+                int out_C, int t_mul, int t_off, int n_split, const void* residual, int out_mode,
+                int act, const void* skip, void* stream);
+
+/* Direct conv for 3-channel planar inputs x bf16 [3, T, H, W] -> channels-last [T, H, W, Cout]:
+ * Encoder3d.conv1 (wan_vae.py:289, kt = 3 causal) and the adaptors' conv_in
+ * (trajectory_module.py:142, kt = 1); weights in the reference layout [Cout, 3, kt, 3, 3].
+ * The input is read as x*in_scale + in_shift (`pseudo*2-1`, infer_vae.py:278). */
+int m4d_conv_in3(const void* x, const void* w, const void* bias, void* out, int T, int H, int W,
+                 int Cout, int kt, float in_scale, float in_shift, void* stream);
+
+/* RMS_norm over channels (* sqrt(C) * gamma) [+ SiLU] per pixel, in place allowed
+ * (wan_vae.py:43-58 + nn.SiLU at :198-202). */
+int m4d_rmsnorm_silu_cl(const void* x, const void* gamma, void* out, long long pixels, int C,
+                        int do_silu, void* stream);
+
+/* nearest-exact 2x spatial upsample [T,H,W,C] -> [T,2H,2W,C] (wan_vae.py:61-67). */
+int m4d_upsample2x_cl(const void* x, void* out, int T, int H, int W, int C, void* stream);
+
+/* planar [C, P] -> channels-last [P, Cpad]; with div/add: z / inv_std + mean (wan_vae.py:682-686). */
+int m4d_planar_to_cl(const void* x, void* out, long long P, int C, int Cpad, const float* div,
+                     const float* add, void* stream);
+
+/* channels-last [P, C] -> planar [C, P]; first n_affine channels get (v - sub) * mul
+ * (wan_vae.py:540-545). */
+int m4d_cl_to_planar(const void* x, void* out, long long P, int C, int n_affine, const float* sub,
+                     const float* mul, void* stream);
+
+/* GroupNorm(32, eps, affine) + x*sigmoid(x) on [F, HW, C] channels-last
+ * (trajectory_module.py:54-60); stats_ws: 64*F floats of scratch. */
+int m4d_groupnorm_swish_cl(const void* x, const void* weight, const void* bias, void* out,
+                           float* stats_ws, int F, int HW, int C, int groups, float eps,
+                           void* stream);
+
+/* p bf16 [rows, N] = softmax(s fp32 [rows, N] * scale) — VAE AttentionBlock (wan_vae.py:257). */
+int m4d_softmax_rows(const float* s, void* p, int rows, int N, long long lds, long long ldp,
+                     float scale, void* stream);
+
+/* out[c, r] = in[r, c] (bf16). */
+int m4d_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in, long long ld_out,
+                       void* stream);
 
 /* out bf16 = SiLU(x fp32), n % 4 == 0 — input of the Motion-Perception-Module projection
  * (wan_transformer4d.py:746-748,781). */

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "libmore4d_sm100.so")
 HEADER_PATH = os.path.join(HERE, "..", "include", "more4d_b200.h")
 
 # epilogue ids (include/more4d_b200.h)
-EPI_BF16, EPI_GELU_TANH, EPI_GELU_ERF, EPI_F32, EPI_GATE_RESIDUAL_F32 = range(5)
+(EPI_BF16, EPI_GELU_TANH, EPI_GELU_ERF, EPI_F32, EPI_GATE_RESIDUAL_F32, EPI_ADD_BF16,
+ EPI_F32_RAW) = range(7)
 
 _P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
 
@@ -39,6 +40,16 @@ _SIGNATURES = {
     "m4d_widen_rows": (c_int, [_P, _P, _I, _I, _I, _L, _I, _P]),
     "m4d_cfg_euler_step": (c_int, [_P, _P, _P, _F, _F, _L, _P]),
     "m4d_silu_bf16": (c_int, [_P, _P, _L, _P]),
+    "m4d_conv_cl": (c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P] + [_I] * 12 + [_P, _I, _I, _I, _I, _P,
+                            _I, _I, _P, _P]),
+    "m4d_conv_in3": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "m4d_rmsnorm_silu_cl": (c_int, [_P, _P, _P, _L, _I, _I, _P]),
+    "m4d_upsample2x_cl": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "m4d_planar_to_cl": (c_int, [_P, _P, _L, _I, _I, _P, _P, _P]),
+    "m4d_cl_to_planar": (c_int, [_P, _P, _L, _I, _I, _P, _P, _P]),
+    "m4d_groupnorm_swish_cl": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "m4d_softmax_rows": (c_int, [_P, _P, _I, _I, _L, _L, _F, _P]),
+    "m4d_transpose_bf16": (c_int, [_P, _P, _I, _I, _L, _L, _P]),
 }
 
 _lib = None

@@ -1,0 +1,446 @@
+// Causal 3-D / 2-D convolution of the Wan VAE and the trajectory adaptors as an implicit GEMM on
+// tcgen05 tensor cores over CHANNELS-LAST activations.
+//
+// Replaces CausalConv3d (MoRe4D/models/wan_vae.py:21-40: torch.cat with the cache + F.pad +
+// cuDNN Conv3d), the Conv2d's of Resample (:82-100) and of the adaptors' ResnetBlocks
+// (MoRe4D/models/trajectory_module.py:73-87).  The reference's chunk loop + 2-frame feature
+// cache is algebraically a causal convolution over the whole sequence (oracle/vae_oracle.py),
+// so the kernel takes the whole [T, H, W, C] sequence and there is no cache, cat, clone or pad
+// copy at all: causal (front) padding in time and zero padding in space are TMA
+// out-of-bounds zero fill of a 4-D tensor map (negative / overshooting box coordinates).
+//
+// GEMM view:  M = output pixels (one tile = 8 rows x 16 cols of one output frame = 128 rows),
+//             N = output channels (tile NT <= 256),   K = taps x Cin.
+// For each tap (a, b, c) and each block of 32 input channels the producer issues ONE TMA box
+// {32 ch, 16 w, 8 h, 1 t} at coordinates shifted by the tap — it lands in shared memory as a
+// K-major 128 x 32 SWIZZLE_64B operand tile, exactly what tcgen05.mma consumes.  Strided convs
+// (downsample) use the tensor map's element strides.  Weights are pre-packed once to
+// [Cout_pad, taps * Cin] (tap-major, channel-minor) so the B tile is a plain 2-D TMA box.
+//
+// CTA = 256 threads, persistent: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (bias, residual add, bf16 rounding like the reference's bf16 path; NHWC
+// store, or planar NCTHW store with clamp / sigmoid for the 3-channel model outputs).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace m4d {
+
+constexpr int CV_TH = 8, CV_TW = 16;           // output tile: 8 x 16 pixels = 128 GEMM rows
+constexpr int CV_KB = 32;                      // channels per TMA box (64 bytes -> SWIZZLE_64B)
+constexpr int CV_A_SUB = 128 * CV_KB * 2;      // 8 KB
+constexpr int CV_THREADS = 256;
+constexpr int CV_SMEM_BUDGET = 200 * 1024;
+
+struct ConvParams {
+  int T_out, H_out, W_out;
+  int Cin, Cout;            // Cin multiple of 32 (as stored), Cout = real output channels
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int ksub;                 // 32-channel boxes per pipeline stage
+  int NT;                   // output-channel tile (multiple of 16, <= 256)
+  int n_tiles;              // ceil(Cout / NT)
+  int stages;
+  // output addressing: element (t, h, w, n) goes to frame t*t_mul + t_off + n / n_split,
+  // channel n % n_split of a channels-last tensor with out_C channels per pixel
+  void* out;
+  const bf16* residual;     // same addressing as out (NHWC mode only), or null
+  const bf16* bias;         // [Cout] or null
+  int out_C, t_mul, t_off, n_split;
+  int out_mode;             // 0 NHWC bf16; 1 planar NCTHW bf16 (n < Cout)
+  int act;                  // 0 none, 1 clamp(-1,1), 2 sigmoid(y + skip)
+  const bf16* skip;         // planar NCTHW tensor added before the sigmoid (act == 2)
+  long long planar_cstride; // T*H*W of the planar tensors
+};
+
+__device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr) {
+  // K-major SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_cl_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int a_bytes = p.ksub * CV_A_SUB;
+  const int b_sub = p.NT * CV_KB * 2;
+  const int stage_bytes = a_bytes + p.ksub * b_sub;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_w = (p.W_out + CV_TW - 1) / CV_TW;
+  const int tiles_h = (p.H_out + CV_TH - 1) / CV_TH;
+  const int tiles = p.T_out * tiles_h * tiles_w * p.n_tiles;
+  const int taps = p.kt * p.kh * p.kw;
+  const int cblocks = p.Cin / (CV_KB * p.ksub);
+  const int ksteps = taps * cblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int r = tile;
+        const int n_blk = r % p.n_tiles; r /= p.n_tiles;
+        const int w_blk = r % tiles_w; r /= tiles_w;
+        const int h_blk = r % tiles_h;
+        const int t = r / tiles_h;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = ks / cblocks, cb = ks - tap * cblocks;
+          const int a = tap / (p.kh * p.kw), bc = tap - a * (p.kh * p.kw);
+          const int b = bc / p.kw, c = bc - b * p.kw;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a_s = smem + stage * stage_bytes;
+          uint8_t* b_s = a_s + a_bytes;
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);
+          const int x0 = w_blk * CV_TW * p.sw + c - p.pw;
+          const int y0 = h_blk * CV_TH * p.sh + b - p.ph;
+          const int t0 = t * p.st + a - p.pt;
+          for (int s = 0; s < p.ksub; ++s) {
+            const int ch = (cb * p.ksub + s) * CV_KB;
+            tma_load_4d(a_s + s * CV_A_SUB, &tmX, &full[stage], ch, x0, y0, t0);
+            tma_load_2d(b_s + s * b_sub, &tmW, &full[stage], tap * p.Cin + ch, n_blk * p.NT);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
+          for (int s = 0; s < p.ksub; ++s) {
+#pragma unroll
+            for (int k = 0; k < CV_KB / 16; ++k) {
+              const uint64_t ad = umma_smem_desc_sw64(a_addr + s * CV_A_SUB + k * 32);
+              const uint64_t bd = umma_smem_desc_sw64(b_addr + s * b_sub + k * 32);
+              umma_ss(d_tmem, ad, bd, idesc, (ks | s | k) != 0);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      int r = tile;
+      const int n_blk = r % p.n_tiles; r /= p.n_tiles;
+      const int w_blk = r % tiles_w; r /= tiles_w;
+      const int h_blk = r % tiles_h;
+      const int t = r / tiles_h;
+      const int h = h_blk * CV_TH + row / CV_TW;
+      const int w = w_blk * CV_TW + row % CV_TW;
+      const bool pix_ok = (h < p.H_out) && (w < p.W_out);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+      for (int c0 = 0; c0 < p.NT; c0 += 32) {
+        const int n0 = n_blk * p.NT + c0;
+        if (n0 >= p.Cout) break;                       // warp-uniform
+        uint32_t rr[32];
+        tmem_ld32(t_row + c0, rr);
+        tmem_ld_wait();
+        if (!pix_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = __uint_as_float(rr[i]);
+          if (p.bias != nullptr && n0 + i < p.Cout) v[i] += __bfloat162float(p.bias[n0 + i]);
+          v[i] = bf16_round(v[i]);
+        }
+        if (p.out_mode == 0) {
+          const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
+          const int ch = n0 % p.n_split;
+          const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off;
+          const int nvalid = min(32, p.Cout - n0);
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            if (p.residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = rp[q];
+                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[q * 8 + 2 * e] += __uint_as_float(ww[e] << 16);
+                  v[q * 8 + 2 * e + 1] += __uint_as_float(ww[e] & 0xFFFF0000u);
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              reinterpret_cast<uint4*>(o)[q] = u;
+            }
+          } else {
+            for (int i = 0; i < nvalid; ++i) {
+              float y = v[i];
+              if (p.residual != nullptr) y += __bfloat162float(p.residual[off + i]);
+              o[i] = __float2bfloat16_rn(y);
+            }
+          }
+        } else {
+          // planar NCTHW output of a few channels (decoder head / adaptor conv_out)
+          const long long pix = (static_cast<long long>(t) * p.H_out + h) * p.W_out + w;
+          for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
+            float y = v[i];
+            const long long off = (n0 + i) * p.planar_cstride + pix;
+            if (p.act == 1) y = fminf(1.f, fmaxf(-1.f, y));
+            if (p.act == 2) {
+              y = bf16_round(y + __bfloat162float(p.skip[off]));
+              y = 1.f / (1.f + __expf(-y));
+            }
+            reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(y);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------
+// Direct convolution for the 3-channel model inputs (Encoder3d.conv1 vae:289, adaptor conv_in
+// traj:142-146): K = 27*3 (or 9*3) is far too thin for tensor cores.  Input planar NCTHW bf16
+// (the module's own input layout, optionally with the `x*2-1` of infer_vae.py:278 fused),
+// output channels-last bf16.  One thread = one output pixel; weights staged in shared memory
+// as fp32.
+// ---------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(128)
+conv_in3_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias,
+                bf16* __restrict__ out, int T, int H, int W, int Cout, float in_scale, float in_shift) {
+  extern __shared__ float wsm[];                 // [Cout][3*KT*9] + bias[Cout]
+  constexpr int KV = 3 * KT * 9;
+  for (int i = threadIdx.x; i < Cout * KV; i += blockDim.x) wsm[i] = __bfloat162float(w[i]);
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x)
+    wsm[Cout * KV + i] = bias ? __bfloat162float(bias[i]) : 0.f;
+  __syncthreads();
+  const int wq = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y, t = blockIdx.z;
+  if (wq >= W) return;
+  const long long plane = static_cast<long long>(T) * H * W;
+  float xin[KV];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int a = 0; a < KT; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int tt = t + a - (KT - 1), hh = h + b - 1, ww = wq + d - 1;
+          float v = 0.f;
+          if (tt >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            v = __bfloat162float(x[c * plane + (static_cast<long long>(tt) * H + hh) * W + ww]);
+            v = bf16_round(bf16_round(v * in_scale) + in_shift);
+          }
+          xin[((c * KT + a) * 3 + b) * 3 + d] = v;
+        }
+  bf16* o = out + ((static_cast<long long>(t) * H + h) * W + wq) * Cout;
+  for (int n = 0; n < Cout; n += 2) {
+    float a0 = wsm[Cout * KV + n], a1 = wsm[Cout * KV + n + 1];
+    const float* w0 = wsm + n * KV;
+    const float* w1 = w0 + KV;
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      a0 = fmaf(xin[k], w0[k], a0);
+      a1 = fmaf(xin[k], w1[k], a1);
+    }
+    *reinterpret_cast<uint32_t*>(o + n) = pack_bf16(a0, a1);
+  }
+}
+
+}  // namespace m4d
+
+using namespace m4d;
+
+extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin, const void* w_packed,
+                           int Cout, int Cout_pad, const void* bias, int kt, int kh, int kw, int st,
+                           int sh, int sw, int pt, int ph, int pw, int T_out, int H_out, int W_out,
+                           void* out, int out_C, int t_mul, int t_off, int n_split,
+                           const void* residual, int out_mode, int act, const void* skip,
+                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && w_packed && out, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(T_in > 0 && H_in > 0 && W_in > 0 && T_out > 0 && H_out > 0 && W_out > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(Cin > 0 && Cin % CV_KB == 0, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(Cout > 0 && Cout_pad >= Cout && Cout_pad % 16 == 0, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && st >= 1 && sh >= 1 && sw >= 1 && sh <= 2 && sw <= 2,
+              M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(out_mode == 0 || out_mode == 1, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(n_split > 0 && out_C > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(act != 2 || skip != nullptr, M4D_ERR_BAD_SHAPE);
+
+  ConvParams p;
+  p.T_out = T_out; p.H_out = H_out; p.W_out = W_out;
+  p.Cin = Cin; p.Cout = Cout;
+  p.kt = kt; p.kh = kh; p.kw = kw; p.st = st; p.sh = sh; p.sw = sw; p.pt = pt; p.ph = ph; p.pw = pw;
+  const int cb32 = Cin / CV_KB;
+  p.ksub = (cb32 % 2 == 0) ? 2 : (cb32 % 3 == 0 ? 3 : 1);
+  // output-channel tile: largest multiple of 16 <= 256 dividing Cout_pad
+  int NT = 16;
+  for (int cand = 256; cand >= 16; cand -= 16)
+    if (Cout_pad % cand == 0) { NT = cand; break; }
+  p.NT = NT;
+  p.n_tiles = Cout_pad / NT;
+  const int stage_bytes = p.ksub * (CV_A_SUB + NT * CV_KB * 2);
+  int stages = CV_SMEM_BUDGET / stage_bytes;
+  p.stages = stages > 6 ? 6 : stages;
+  M4D_REQUIRE(p.stages >= 2, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(n_split % 32 == 0 || n_split >= Cout, M4D_ERR_UNSUPPORTED);
+  p.out = out;
+  p.residual = static_cast<const bf16*>(residual);
+  p.bias = static_cast<const bf16*>(bias);
+  p.out_C = out_C; p.t_mul = t_mul; p.t_off = t_off; p.n_split = n_split;
+  p.out_mode = out_mode; p.act = act;
+  p.skip = static_cast<const bf16*>(skip);
+  p.planar_cstride = static_cast<long long>(T_out) * H_out * W_out;
+
+  CUtensorMap tmX, tmW;
+  {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return M4D_ERR_NO_DEVICE;
+    if (!aligned16(x)) return M4D_ERR_ALIGN;
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(W_in),
+                          static_cast<cuuint64_t>(H_in), static_cast<cuuint64_t>(T_in)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(Cin) * 2, static_cast<cuuint64_t>(W_in) * Cin * 2,
+                          static_cast<cuuint64_t>(H_in) * W_in * Cin * 2};
+    cuuint32_t box[4] = {CV_KB, static_cast<cuuint32_t>(CV_TW * sw), static_cast<cuuint32_t>(CV_TH * sh), 1};
+    cuuint32_t es[4] = {1, static_cast<cuuint32_t>(sw), static_cast<cuuint32_t>(sh), 1};
+    CUresult r = fn(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box,
+                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[more4d_b200] conv: cuTensorMapEncodeTiled(X) failed: %d\n", static_cast<int>(r));
+      return M4D_ERR_CUDA;
+    }
+    if (!aligned16(w_packed)) return M4D_ERR_ALIGN;
+    const long long Ktot = static_cast<long long>(kt) * kh * kw * Cin;
+    cuuint64_t wdim[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Cout_pad)};
+    cuuint64_t wstr[1] = {static_cast<cuuint64_t>(Ktot) * 2};
+    cuuint32_t wbox[2] = {CV_KB, static_cast<cuuint32_t>(NT)};
+    cuuint32_t wes[2] = {1, 1};
+    r = fn(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), wdim, wstr, wbox,
+           wes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[more4d_b200] conv: cuTensorMapEncodeTiled(W) failed: %d\n", static_cast<int>(r));
+      return M4D_ERR_CUDA;
+    }
+  }
+  const int smem_bytes = p.stages * stage_bytes + 256 + 1024;
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    int rc = cuda_ok(cudaFuncSetAttribute(conv_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          CV_SMEM_BUDGET + 256 + 1024 + 16 * 1024),
+                     "cudaFuncSetAttribute(conv)");
+    if (rc != M4D_OK) return rc;
+    configured = CV_SMEM_BUDGET + 256 + 1024 + 16 * 1024;
+  }
+  const long long tiles = static_cast<long long>(T_out) * ((H_out + CV_TH - 1) / CV_TH) *
+                          ((W_out + CV_TW - 1) / CV_TW) * p.n_tiles;
+  M4D_REQUIRE(tiles < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  const int grid = tiles < sm_count() ? static_cast<int>(tiles) : sm_count();
+  conv_cl_kernel<<<grid, CV_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
+  M4D_CHECK_LAUNCH("conv_cl_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_conv_in3(const void* x, const void* w, const void* bias, void* out, int T, int H,
+                            int W, int Cout, int kt, float in_scale, float in_shift, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && w && out && T > 0 && H > 0 && W > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE((kt == 1 || kt == 3) && Cout > 0 && Cout % 2 == 0, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(H <= 65535 && T <= 65535, M4D_ERR_BAD_SHAPE);
+  const int smem = (Cout * 3 * kt * 9 + Cout) * 4;
+  dim3 grid((W + 127) / 128, H, T);
+  if (kt == 3) {
+    static bool cfgd = false;
+    if (!cfgd) {
+      int rc = cuda_ok(cudaFuncSetAttribute(conv_in3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            96 * 1024), "cudaFuncSetAttribute(conv_in3)");
+      if (rc != M4D_OK) return rc;
+      cfgd = true;
+    }
+    M4D_REQUIRE(smem <= 96 * 1024, M4D_ERR_UNSUPPORTED);
+    conv_in3_kernel<3><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(w),
+                                                    static_cast<const bf16*>(bias), static_cast<bf16*>(out),
+                                                    T, H, W, Cout, in_scale, in_shift);
+  } else {
+    M4D_REQUIRE(smem <= 48 * 1024, M4D_ERR_UNSUPPORTED);
+    conv_in3_kernel<1><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(w),
+                                                    static_cast<const bf16*>(bias), static_cast<bf16*>(out),
+                                                    T, H, W, Cout, in_scale, in_shift);
+  }
+  M4D_CHECK_LAUNCH("conv_in3_kernel");
+  return M4D_OK;
+}

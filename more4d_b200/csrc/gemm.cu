@@ -56,7 +56,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
   const bool full = (n0 + 32 <= N);
-  if (ep.bias != nullptr) {
+  if (EPI != M4D_EPI_F32_RAW && ep.bias != nullptr) {
     if (full) {
       const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + n0);
 #pragma unroll
@@ -76,8 +76,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
     }
   }
   // the Linear output is a bf16 tensor on the reference path
+  if (EPI != M4D_EPI_F32_RAW) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+  }
   if (EPI == M4D_EPI_GELU_TANH) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
@@ -87,7 +89,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
   }
   if (!row_ok) return;
 
-  if (EPI == M4D_EPI_GATE_RESIDUAL_F32 || EPI == M4D_EPI_F32) {
+  if (EPI == M4D_EPI_GATE_RESIDUAL_F32 || EPI == M4D_EPI_F32 || EPI == M4D_EPI_F32_RAW) {
     float* orow = reinterpret_cast<float*>(ep.out) + m * ep.ldo + n0;
     if (EPI == M4D_EPI_GATE_RESIDUAL_F32) {
       const float* rrow = ep.res + m * ep.ldr + n0;
@@ -123,6 +125,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
     }
   } else {
     bf16* orow = reinterpret_cast<bf16*>(ep.out) + m * ep.ldo + n0;
+    if (EPI == M4D_EPI_ADD_BF16) {
+      const bf16* rrow = reinterpret_cast<const bf16*>(ep.res) + m * ep.ldr + n0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < N) v[i] += __bfloat162float(rrow[i]);
+    }
     if (full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -291,9 +299,10 @@ using namespace m4d;
 
 extern "C" int m4d_gemm_bf16(const void* a, long long lda, const void* w, long long ldw,
                              const void* bias, void* out, long long ldo, int M, int N, int K,
-                             int epilogue, const float* residual, long long ldr, const float* gate,
+                             int epilogue, const void* residual_, long long ldr, const float* gate,
                              long long gate_batch_stride, int rows_per_batch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const float* residual = static_cast<const float*>(residual_);
   M4D_REQUIRE(M > 0 && N > 0 && K > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(a && w && out, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, M4D_ERR_ALIGN);
@@ -306,8 +315,9 @@ extern "C" int m4d_gemm_bf16(const void* a, long long lda, const void* w, long l
                     gate_batch_stride % 4 == 0,
                 M4D_ERR_ALIGN);
   }
-  if (epilogue == M4D_EPI_GATE_RESIDUAL_F32 || epilogue == M4D_EPI_F32)
+  if (epilogue == M4D_EPI_GATE_RESIDUAL_F32 || epilogue == M4D_EPI_F32 || epilogue == M4D_EPI_F32_RAW)
     M4D_REQUIRE(aligned16(out) && ldo % 4 == 0, M4D_ERR_ALIGN);
+  if (epilogue == M4D_EPI_ADD_BF16) M4D_REQUIRE(residual != nullptr && ldr >= N, M4D_ERR_BAD_SHAPE);
   if (bias) M4D_REQUIRE(aligned16(bias), M4D_ERR_ALIGN);
 
   CUtensorMap tmA, tmB;
@@ -341,6 +351,8 @@ extern "C" int m4d_gemm_bf16(const void* a, long long lda, const void* w, long l
     case M4D_EPI_F32: return launch_gemm<M4D_EPI_F32>(tmA, tmB, M, N, K, ep, stream);
     case M4D_EPI_GATE_RESIDUAL_F32:
       return launch_gemm<M4D_EPI_GATE_RESIDUAL_F32>(tmA, tmB, M, N, K, ep, stream);
+    case M4D_EPI_ADD_BF16: return launch_gemm<M4D_EPI_ADD_BF16>(tmA, tmB, M, N, K, ep, stream);
+    case M4D_EPI_F32_RAW: return launch_gemm<M4D_EPI_F32_RAW>(tmA, tmB, M, N, K, ep, stream);
   }
   return M4D_ERR_UNSUPPORTED;
 }

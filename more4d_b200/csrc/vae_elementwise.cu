@@ -1,0 +1,332 @@
+// HBM-bound kernels of the VAE / adaptor path on channels-last bf16 activations [P pixels, C]:
+// everything between the convolutions.  The reference runs each as several eager passes over
+// permuted copies (SURVEY.md K17-K21, §3.3 iv); here each is one read + one write.
+// Rounding follows the reference's bf16 inference path (fp32 statistics inside, every tensor
+// op's result rounded to bf16 — oracle/vae_oracle.py emulate_bf16).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace m4d {
+
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y);
+  u.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(x / (1.f + __expf(-x))); }
+
+// RMS_norm (wan_vae.py:43-58: F.normalize over channels * sqrt(C) * gamma) [+ SiLU], one warp
+// per pixel, C <= 512, C % 4 == 0.  May run in place.
+__global__ void __launch_bounds__(256)
+rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, bf16* __restrict__ out,
+                       long long pixels, int C, int do_silu) {
+  const long long pix = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= pixels) return;
+  const bf16* xr = x + pix * C;
+  const int nvec = C >> 2;
+  float4 v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      v[i] = ld4(xr + vi * 4);
+      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float nrm = fmaxf(bf16_round(sqrtf(wsum(ss))), 1e-12f);
+  const float sc = sqrtf(static_cast<float>(C));
+  bf16* orow = out + pix * C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g = ld4(gamma + vi * 4);
+      float4 y;
+      y.x = bf16_round(bf16_round(bf16_round(v[i].x / nrm) * sc) * g.x);
+      y.y = bf16_round(bf16_round(bf16_round(v[i].y / nrm) * sc) * g.y);
+      y.z = bf16_round(bf16_round(bf16_round(v[i].z / nrm) * sc) * g.z);
+      y.w = bf16_round(bf16_round(bf16_round(v[i].w / nrm) * sc) * g.w);
+      if (do_silu) {
+        y.x = silu_bf16r(y.x); y.y = silu_bf16r(y.y); y.z = silu_bf16r(y.z); y.w = silu_bf16r(y.w);
+      }
+      st4(orow + vi * 4, y);
+    }
+  }
+}
+
+// nearest-exact 2x spatial upsample (wan_vae.py:61-67,82-83) on [T, H, W, C] -> [T, 2H, 2W, C]
+__global__ void upsample2x_cl_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, int H,
+                                     int W, int C8) {
+  // one thread = one 16-byte vector of one OUTPUT pixel
+  const long long total = static_cast<long long>(T) * 2 * H * 2 * W * C8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  long long r = idx / C8;
+  const int wo = static_cast<int>(r % (2 * W)); r /= 2 * W;
+  const int ho = static_cast<int>(r % (2 * H));
+  const int t = static_cast<int>(r / (2 * H));
+  const uint4* src = reinterpret_cast<const uint4*>(x) +
+                     ((static_cast<long long>(t) * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c;
+  reinterpret_cast<uint4*>(out)[idx] = __ldg(src);
+}
+
+// planar [C, T, H, W] -> channels-last [T*H*W, Cpad] (zero-padded channels) with the decoder's
+// latent de-normalisation z / inv_std + mean (wan_vae.py:682-686) fused when `div` is given.
+__global__ void planar_to_cl_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long P,
+                                    int C, int Cpad, const float* __restrict__ div,
+                                    const float* __restrict__ add) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= P * Cpad) return;
+  const int c = static_cast<int>(idx % Cpad);
+  const long long pix = idx / Cpad;
+  float v = 0.f;
+  if (c < C) {
+    v = __bfloat162float(x[c * P + pix]);
+    if (div != nullptr) v = bf16_round(bf16_round(v / div[c]) + add[c]);
+  }
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+// channels-last [P, C] -> planar [C, P] with the encoder's (mu - mean) * inv_std
+// (wan_vae.py:540-545) on the first n_affine channels.
+__global__ void cl_to_planar_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long P,
+                                    int C, int n_affine, const float* __restrict__ sub,
+                                    const float* __restrict__ mul) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= P * C) return;
+  const long long pix = idx % P;
+  const int c = static_cast<int>(idx / P);
+  float v = __bfloat162float(x[pix * C + c]);
+  if (c < n_affine) v = bf16_round(bf16_round(v - sub[c]) * mul[c]);
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+// GroupNorm(32 groups, eps 1e-6, affine) + swish for the adaptors (trajectory_module.py:54-60)
+// on [F, HW, C] channels-last, statistics per (frame, group).  Pass 1: partial sums.
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int HW, int C, int cpg) {
+  // grid (chunks, F); thread handles channel-vector v = tid % (C/4) of pixels tid / (C/4) + k*ppb
+  __shared__ float sh[2 * 32 * 8];
+  const int nvec = C >> 2;
+  const int f = blockIdx.y;
+  const int v = threadIdx.x % nvec;
+  const int ppb = blockDim.x / nvec;
+  float s = 0.f, ss = 0.f;
+  if (threadIdx.x < ppb * nvec) {
+    for (int pix = blockIdx.x * ppb + threadIdx.x / nvec; pix < HW; pix += gridDim.x * ppb) {
+      const float4 a = ld4(x + (static_cast<long long>(f) * HW + pix) * C + v * 4);
+      s += (a.x + a.y) + (a.z + a.w);
+      ss += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+    }
+  }
+  // a group spans cpg channels = cpg/4 vectors (cpg is a multiple of 4)
+  const int g = (v * 4) / cpg;
+  for (int i = threadIdx.x; i < 2 * 32 * 8; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (threadIdx.x < ppb * nvec) {
+    atomicAdd(&sh[(g * 2 + 0) * 8 + (threadIdx.x & 7)], s);
+    atomicAdd(&sh[(g * 2 + 1) * 8 + (threadIdx.x & 7)], ss);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[threadIdx.x * 8 + i];
+    atomicAdd(&stats[f * 64 + threadIdx.x], t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                       const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ out,
+                       int F, int HW, int C, int cpg, float eps) {
+  const long long nvec_total = static_cast<long long>(F) * HW * (C >> 2);
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nvec_total) return;
+  const int nvec = C >> 2;
+  const int v = static_cast<int>(idx % nvec);
+  const int f = static_cast<int>(idx / (static_cast<long long>(HW) * nvec));
+  const int g = (v * 4) / cpg;
+  const float n = static_cast<float>(HW) * cpg;
+  const float mean = stats[f * 64 + g * 2] / n;
+  const float var = fmaxf(stats[f * 64 + g * 2 + 1] / n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float4 a = ld4(x + idx * 4), ww = ld4(w + v * 4), bb = ld4(b + v * 4);
+  float4 y;
+  y.x = bf16_round((a.x - mean) * rstd * ww.x + bb.x);
+  y.y = bf16_round((a.y - mean) * rstd * ww.y + bb.y);
+  y.z = bf16_round((a.z - mean) * rstd * ww.z + bb.z);
+  y.w = bf16_round((a.w - mean) * rstd * ww.w + bb.w);
+  y.x *= bf16_round(1.f / (1.f + __expf(-y.x)));
+  y.y *= bf16_round(1.f / (1.f + __expf(-y.y)));
+  y.z *= bf16_round(1.f / (1.f + __expf(-y.z)));
+  y.w *= bf16_round(1.f / (1.f + __expf(-y.w)));
+  st4(out + idx * 4, y);
+}
+
+// row softmax of fp32 logits * scale -> bf16 probabilities (the VAE AttentionBlock's single
+// 384-wide head, wan_vae.py:257-261, run as GEMM -> softmax -> GEMM)
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int N, long long lds,
+                    long long ldp, float scale) {
+  __shared__ float red[8];
+  const float* sr = s + static_cast<long long>(blockIdx.x) * lds;
+  bf16* pr = p + static_cast<long long>(blockIdx.x) * ldp;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sum += __expf((sr[i] - mx) * scale);
+  sum = wsum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    pr[i] = __float2bfloat16_rn(__expf((sr[i] - mx) * scale) * inv);
+}
+
+// out[c, r] = in[r, c]  (bf16), 32x32 smem tiles; in row stride ld_in, out row stride ld_out
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int C,
+                                      long long ld_in, long long ld_out) {
+  __shared__ bf16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[i][threadIdx.x] = in[r * ld_in + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace m4d
+
+using namespace m4d;
+
+extern "C" int m4d_rmsnorm_silu_cl(const void* x, const void* gamma, void* out, long long pixels,
+                                   int C, int do_silu, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && gamma && out && pixels > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(C % 4 == 0 && C <= 512 && C > 0, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+              M4D_ERR_ALIGN);
+  const long long blocks = (pixels + 7) / 8;
+  M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  rmsnorm_silu_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<const bf16*>(gamma), static_cast<bf16*>(out), pixels, C,
+      do_silu);
+  M4D_CHECK_LAUNCH("rmsnorm_silu_cl_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_upsample2x_cl(const void* x, void* out, int T, int H, int W, int C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && out && T > 0 && H > 0 && W > 0 && C > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(out), M4D_ERR_ALIGN);
+  const long long total = static_cast<long long>(T) * 4 * H * W * (C / 8);
+  const long long blocks = (total + 255) / 256;
+  M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  upsample2x_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C / 8);
+  M4D_CHECK_LAUNCH("upsample2x_cl_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_planar_to_cl(const void* x, void* out, long long P, int C, int Cpad,
+                                const float* div, const float* add, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && out && P > 0 && C > 0 && Cpad >= C, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE((div == nullptr) == (add == nullptr), M4D_ERR_BAD_SHAPE);
+  const long long blocks = (P * Cpad + 255) / 256;
+  M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  planar_to_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), P, C, Cpad, div, add);
+  M4D_CHECK_LAUNCH("planar_to_cl_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_cl_to_planar(const void* x, void* out, long long P, int C, int n_affine,
+                                const float* sub, const float* mul, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && out && P > 0 && C > 0 && n_affine >= 0 && n_affine <= C, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(n_affine == 0 || (sub && mul), M4D_ERR_BAD_SHAPE);
+  const long long blocks = (P * C + 255) / 256;
+  M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  cl_to_planar_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), P, C, n_affine, sub, mul);
+  M4D_CHECK_LAUNCH("cl_to_planar_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_groupnorm_swish_cl(const void* x, const void* weight, const void* bias, void* out,
+                                      float* stats_ws, int F, int HW, int C, int groups, float eps,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && weight && bias && out && stats_ws && F > 0 && HW > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(groups == 32 && C % (groups * 4) == 0 && C <= 1024, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(F <= 65535, M4D_ERR_BAD_SHAPE);
+  int rc = cuda_ok(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 64 * F, stream), "memset(groupnorm stats)");
+  if (rc != M4D_OK) return rc;
+  const int cpg = C / groups;
+  const int ppb = 256 / (C / 4);
+  int chunks = (HW + ppb * 16 - 1) / (ppb * 16);
+  if (chunks > 1024) chunks = 1024;
+  if (chunks < 1) chunks = 1;
+  groupnorm_stats_kernel<<<dim3(chunks, F), 256, 0, stream>>>(static_cast<const bf16*>(x), stats_ws, HW, C, cpg);
+  M4D_CHECK_LAUNCH("groupnorm_stats_kernel");
+  const long long nvec = static_cast<long long>(F) * HW * (C / 4);
+  const long long blocks = (nvec + 255) / 256;
+  M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  groupnorm_swish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), stats_ws, static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),
+      static_cast<bf16*>(out), F, HW, C, cpg, eps);
+  M4D_CHECK_LAUNCH("groupnorm_swish_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_softmax_rows(const float* s, void* p, int rows, int N, long long lds, long long ldp,
+                                float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(s && p && rows > 0 && N > 0 && lds >= N && ldp >= N, M4D_ERR_BAD_SHAPE);
+  softmax_rows_kernel<<<rows, 256, 0, stream>>>(s, static_cast<bf16*>(p), N, lds, ldp, scale);
+  M4D_CHECK_LAUNCH("softmax_rows_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in,
+                                  long long ld_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(in && out && R > 0 && C > 0 && ld_in >= C && ld_out >= R, M4D_ERR_BAD_SHAPE);
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  M4D_REQUIRE(grid.y <= 65535, M4D_ERR_BAD_SHAPE);
+  transpose_bf16_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const bf16*>(in), static_cast<bf16*>(out),
+                                                          R, C, ld_in, ld_out);
+  M4D_CHECK_LAUNCH("transpose_bf16_kernel");
+  return M4D_OK;
+}

@@ -7,8 +7,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_BF16, EPI_F32, EPI_GATE_RESIDUAL_F32, EPI_GELU_ERF,  # noqa: F401
-                   EPI_GELU_TANH)
+from ._lib import (EPI_ADD_BF16, EPI_BF16, EPI_F32, EPI_F32_RAW,  # noqa: F401
+                   EPI_GATE_RESIDUAL_F32, EPI_GELU_ERF, EPI_GELU_TANH)
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -71,7 +71,7 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: i
     if weight.stride(-1) != 1:
         raise ValueError("more4d_b200.linear: weight rows must be contiguous")
     M = x2.shape[0]
-    f32_out = epilogue in (EPI_F32, EPI_GATE_RESIDUAL_F32)
+    f32_out = epilogue in (EPI_F32, EPI_GATE_RESIDUAL_F32, EPI_F32_RAW)
     if out is None:
         out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32 if f32_out else BF16)
     _req(out, torch.float32 if f32_out else BF16, "out")
@@ -86,6 +86,11 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: i
         res2 = residual.reshape(-1, N)
         if gate is not None:
             _req(gate, torch.float32, "gate")
+    elif epilogue == EPI_ADD_BF16:
+        if residual is None:
+            raise ValueError("more4d_b200.linear: residual required")
+        _req(residual, BF16, "residual")
+        res2 = residual.reshape(-1, N)
     if bias is not None:
         _req(bias, BF16, "bias")
     rc = _lib.lib().m4d_gemm_bf16(
@@ -288,4 +293,160 @@ def silu_bf16(x: Tensor) -> Tensor:
     out = torch.empty(x.shape, device=x.device, dtype=BF16)
     rc = _lib.lib().m4d_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     _lib.check(rc, "m4d_silu_bf16")
+    return out
+
+
+# ======================================================================================
+# Motion-Sensitive VAE ops (channels-last bf16 activations [T, H, W, C])
+# ======================================================================================
+def pack_conv_weight(w: Tensor) -> Tensor:
+    """Reference conv weight [Cout, Cin, (kt,) kh, kw] -> implicit-GEMM operand
+    [Cout_pad16, taps * Cin_pad32] (tap-major, channel-minor, zero padded).  One-time weight
+    preprocessing, not on the per-call path."""
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    cout, cin, kt, kh, kw = w.shape
+    cin_p, cout_p = (cin + 31) // 32 * 32, (cout + 15) // 16 * 16
+    p = torch.zeros(cout_p, kt, kh, kw, cin_p, device=w.device, dtype=BF16)
+    p[:cout, :, :, :, :cin] = w.permute(0, 2, 3, 4, 1).to(BF16)
+    return p.reshape(cout_p, kt * kh * kw * cin_p).contiguous()
+
+
+def conv_cl(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kernel, stride=(1, 1, 1),
+            pad=(0, 0, 0), t_out: Optional[int] = None, out: Optional[Tensor] = None,
+            t_mul: int = 1, t_off: int = 0, n_split: Optional[int] = None,
+            residual: Optional[Tensor] = None, planar_out: Optional[Tensor] = None, act: int = 0,
+            skip: Optional[Tensor] = None) -> Tensor:
+    """Implicit-GEMM convolution over a channels-last sequence x [T, H, W, Cin] (Cin % 32 == 0).
+    `pad` = (front frames, top/left rows, cols); right/bottom/behind padding is implied by the
+    output size.  Returns the channels-last output (or `planar_out` [Cout, T, H, W])."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    if not x.is_contiguous():
+        raise ValueError("more4d_b200.conv_cl: x must be contiguous [T, H, W, C]")
+    T, H, W, Cin = x.shape
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = pad
+    if w_packed.shape[1] != kt * kh * kw * Cin:
+        raise ValueError("more4d_b200.conv_cl: packed weight does not match (taps, Cin)")
+    H_out = (H + (2 * ph if sh == 1 else 1) - kh) // sh + 1
+    W_out = (W + (2 * pw if sw == 1 else 1) - kw) // sw + 1
+    if t_out is None:
+        t_out = (T + pt - kt) // st + 1
+    out_mode = 0
+    if planar_out is not None:
+        _req(planar_out, BF16, "planar_out")
+        out_t, out_mode, out_C = planar_out, 1, cout
+        n_split = n_split or max(cout, 32)
+    else:
+        if out is None:
+            out = torch.empty(t_out, H_out, W_out, cout, device=x.device, dtype=BF16)
+        _req(out, BF16, "out")
+        out_t, out_C = out, out.shape[-1]
+        n_split = n_split or max(out_C, cout)
+    rc = _lib.lib().m4d_conv_cl(
+        x.data_ptr(), T, H, W, Cin, w_packed.data_ptr(), cout, w_packed.shape[0], _ptr(bias),
+        kt, kh, kw, st, sh, sw, pt, ph, pw, t_out, H_out, W_out, out_t.data_ptr(), out_C, t_mul, t_off,
+        n_split, _ptr(residual), out_mode, act, _ptr(skip), _stream())
+    _lib.check(rc, "m4d_conv_cl")
+    return out_t
+
+
+def conv_in3(x_planar: Tensor, w: Tensor, bias: Optional[Tensor], kt: int, in_scale: float = 1.0,
+             in_shift: float = 0.0) -> Tensor:
+    """x [3, T, H, W] planar bf16 -> channels-last [T, H, W, Cout] (causal in time for kt = 3)."""
+    _lib.require_device()
+    _req(x_planar, BF16, "x")
+    x_planar = x_planar.contiguous()
+    _, T, H, W = x_planar.shape
+    cout = w.shape[0]
+    out = torch.empty(T, H, W, cout, device=x_planar.device, dtype=BF16)
+    rc = _lib.lib().m4d_conv_in3(x_planar.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), T, H, W,
+                                 cout, kt, in_scale, in_shift, _stream())
+    _lib.check(rc, "m4d_conv_in3")
+    return out
+
+
+def rmsnorm_silu_cl(x: Tensor, gamma: Tensor, silu: bool = True, inplace: bool = False) -> Tensor:
+    _lib.require_device()
+    _req(x, BF16, "x")
+    C = x.shape[-1]
+    out = x if inplace else torch.empty_like(x)
+    rc = _lib.lib().m4d_rmsnorm_silu_cl(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), x.numel() // C,
+                                        C, int(silu), _stream())
+    _lib.check(rc, "m4d_rmsnorm_silu_cl")
+    return out
+
+
+def upsample2x_cl(x: Tensor) -> Tensor:
+    _lib.require_device()
+    _req(x, BF16, "x")
+    T, H, W, C = x.shape
+    out = torch.empty(T, 2 * H, 2 * W, C, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_upsample2x_cl(x.data_ptr(), out.data_ptr(), T, H, W, C, _stream())
+    _lib.check(rc, "m4d_upsample2x_cl")
+    return out
+
+
+def planar_to_cl(x: Tensor, cpad: int, div: Optional[Tensor] = None, add: Optional[Tensor] = None) -> Tensor:
+    """[C, T, H, W] -> [T, H, W, cpad] (zero-padded channels), optional per-channel x/div + add."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    x = x.contiguous()
+    C, T, H, W = x.shape
+    out = torch.empty(T, H, W, cpad, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_planar_to_cl(x.data_ptr(), out.data_ptr(), T * H * W, C, cpad, _ptr(div), _ptr(add),
+                                     _stream())
+    _lib.check(rc, "m4d_planar_to_cl")
+    return out
+
+
+def cl_to_planar(x: Tensor, n_affine: int = 0, sub: Optional[Tensor] = None,
+                 mul: Optional[Tensor] = None) -> Tensor:
+    """[T, H, W, C] -> [C, T, H, W]; the first n_affine channels get (v - sub) * mul."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    T, H, W, C = x.shape
+    out = torch.empty(C, T, H, W, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_cl_to_planar(x.data_ptr(), out.data_ptr(), T * H * W, C, n_affine, _ptr(sub),
+                                     _ptr(mul), _stream())
+    _lib.check(rc, "m4d_cl_to_planar")
+    return out
+
+
+def groupnorm_swish_cl(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-6, groups: int = 32,
+                       inplace: bool = False) -> Tensor:
+    """GroupNorm + swish on [F, H, W, C] with per-frame statistics."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    F_, H, W, C = x.shape
+    out = x if inplace else torch.empty_like(x)
+    ws = torch.empty(64 * F_, device=x.device, dtype=torch.float32)
+    _Stats.launches += 1                                   # stats + apply = two kernels
+    rc = _lib.lib().m4d_groupnorm_swish_cl(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                           ws.data_ptr(), F_, H * W, C, groups, eps, _stream())
+    _lib.check(rc, "m4d_groupnorm_swish_cl")
+    return out
+
+
+def softmax_rows(s: Tensor, scale: float) -> Tensor:
+    _lib.require_device()
+    _req(s, torch.float32, "s")
+    R, N = s.shape
+    p = torch.empty(R, N, device=s.device, dtype=BF16)
+    rc = _lib.lib().m4d_softmax_rows(s.data_ptr(), p.data_ptr(), R, N, s.stride(0), p.stride(0), scale,
+                                     _stream())
+    _lib.check(rc, "m4d_softmax_rows")
+    return p
+
+
+def transpose_bf16(x: Tensor) -> Tensor:
+    """[R, C] (row stride free) -> contiguous [C, R]."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    R, C = x.shape
+    out = torch.empty(C, R, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_transpose_bf16(x.data_ptr(), out.data_ptr(), R, C, x.stride(0), R, _stream())
+    _lib.check(rc, "m4d_transpose_bf16")
     return out

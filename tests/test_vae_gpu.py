@@ -1,0 +1,212 @@
+"""GPU parity of the Motion-Sensitive VAE path (through the C ABI) against the CPU oracle and the
+golden vectors produced by the real reference VAE (chunked, with its feature cache).
+
+Tolerances (relative Frobenius error):
+  * single kernels vs the oracle's bf16-emulation: <= 3e-3 (bf16 output rounding ~1e-3 plus
+    summation-order disagreements of 1 bf16 ulp);
+  * whole encoder / decoder / adaptors: ~30-60 bf16 convolutions deep, every layer's output is
+    re-rounded to bf16, so 1-ulp disagreements compound: <= 3e-2 vs the bf16-emulating oracle
+    and vs the fp32 reference golden.  (The reference's own bf16 CUDA path differs from its fp32
+    path by the same order: the oracle's emulation mode measures that on CPU.)
+"""
+import pytest
+import torch
+
+from more4d_b200 import synth
+from oracle import vae_oracle as V
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+SEED = 11
+
+
+def _rand(shape, seed, scale=1.0, dtype=BF16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+def _cl(x):            # [1, C, T, H, W] -> channels-last [T, H, W, C] on the GPU
+    return x[0].permute(1, 2, 3, 0).contiguous().cuda()
+
+
+def _ncthw(y):         # channels-last GPU -> [1, C, T, H, W] fp32 CPU
+    return y.permute(3, 0, 1, 2).unsqueeze(0).float().cpu()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from more4d_b200 import ops as _ops
+    return _ops
+
+
+AR = V.Arith(True)
+
+
+@pytest.mark.parametrize("cin,cout,T,H,W", [
+    (96, 96, 3, 12, 20),      # ksub = 3, NT = 96, ragged H/W tiles
+    (32, 192, 2, 8, 16),      # exactly one tile, NT = 192
+    (192, 384, 2, 9, 17),     # ksub = 2, two N tiles of 192
+    (384, 32, 1, 16, 32),     # encoder head shape (Cout 32)
+])
+def test_conv3d_causal(ops, cin, cout, T, H, W):
+    x = _rand((1, cin, T, H, W), 1)
+    w = _rand((cout, cin, 3, 3, 3), 2, (cin * 27) ** -0.5)
+    b = _rand((cout,), 3, 0.1)
+    ref = V.causal_conv3d(x.float(), w, b, AR)
+    y = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda()), b.cuda(), cout, (3, 3, 3), pad=(2, 1, 1))
+    assert rel_err(_ncthw(y), ref) < 3e-3
+
+
+def test_conv_residual_and_pointwise(ops):
+    cin, cout, T, H, W = 96, 192, 2, 10, 18
+    x = _rand((1, cin, T, H, W), 4)
+    w1 = _rand((cout, cin, 1, 1, 1), 5, cin ** -0.5)
+    b1 = _rand((cout,), 6, 0.1)
+    h = V.causal_conv3d(x.float(), w1, b1, AR)
+    hg = ops.conv_cl(_cl(x), ops.pack_conv_weight(w1.cuda()), b1.cuda(), cout, (1, 1, 1))
+    assert rel_err(_ncthw(hg), h) < 3e-3
+    w = _rand((cout, cin, 3, 3, 3), 7, (cin * 27) ** -0.5)
+    ref = AR.r(V.causal_conv3d(x.float(), w, b1, AR) + _ncthw(hg))
+    y = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda()), b1.cuda(), cout, (3, 3, 3), pad=(2, 1, 1),
+                    residual=hg)
+    assert rel_err(_ncthw(y), ref) < 3e-3
+
+
+def test_conv2d_stride2_downsample(ops):
+    c, T, H, W = 96, 2, 12, 20
+    x = _rand((1, c, T, H, W), 8)
+    w = _rand((c, c, 3, 3), 9, (c * 9) ** -0.5)
+    b = _rand((c,), 10, 0.1)
+    ref = V.conv2d_frames(x.float(), w, b, AR, stride=2, pad=(0, 1, 0, 1))
+    y = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda()), b.cuda(), c, (1, 3, 3), stride=(1, 2, 2))
+    assert tuple(y.shape) == (T, 6, 10, c)
+    assert rel_err(_ncthw(y), ref) < 3e-3
+
+
+def test_time_conv_down_and_up(ops):
+    c, T, H, W = 64, 5, 8, 16
+    x = _rand((1, c, T, H, W), 11)
+    w = _rand((c, c, 3, 1, 1), 12, (c * 3) ** -0.5)
+    b = _rand((c,), 13, 0.1)
+    sd = {"p.resample.1.weight": torch.zeros(c, c, 3, 3), "p.resample.1.bias": torch.zeros(c),
+          "p.time_conv.weight": w, "p.time_conv.bias": b}
+    # downsample3d temporal part: frame 0 passes through, then stride-2 windows
+    rest = V.causal_conv3d(x.float(), w, b, AR, stride_t=2)
+    out = torch.empty(3, H, W, c, device="cuda", dtype=BF16)
+    xg = _cl(x)
+    out[0].copy_(xg[0])
+    ops.conv_cl(xg, ops.pack_conv_weight(w.cuda()), b.cuda(), c, (3, 1, 1), stride=(2, 1, 1), t_out=2,
+                out=out, t_off=1)
+    assert rel_err(_ncthw(out)[:, :, 1:], rest) < 3e-3
+    assert torch.equal(out[0], xg[0])
+    # upsample3d temporal part: frame 0 invisible, 2C channels interleaved into frames
+    w2 = _rand((2 * c, c, 3, 1, 1), 14, (c * 3) ** -0.5)
+    b2 = _rand((2 * c,), 15, 0.1)
+    u = V.causal_conv3d(x[:, :, 1:].float(), w2, b2, AR).reshape(1, 2, c, T - 1, H, W)
+    ref = torch.stack((u[:, 0], u[:, 1]), 3).reshape(1, c, 2 * (T - 1), H, W)
+    ug = torch.empty(1 + 2 * (T - 1), H, W, c, device="cuda", dtype=BF16)
+    ug[0].copy_(xg[0])
+    ops.conv_cl(xg[1:], ops.pack_conv_weight(w2.cuda()), b2.cuda(), 2 * c, (3, 1, 1), pad=(2, 0, 0),
+                t_out=T - 1, out=ug, t_mul=2, t_off=1, n_split=c)
+    assert rel_err(_ncthw(ug)[:, :, 1:], ref) < 3e-3
+
+
+def test_conv_in3_and_planar_out(ops):
+    T, H, W = 3, 10, 150
+    x = _rand((1, 3, T, H, W), 16, 0.5)
+    w = _rand((96, 3, 3, 3, 3), 17, 81 ** -0.5)
+    b = _rand((96,), 18, 0.1)
+    ref = V.causal_conv3d(AR.r(AR.r(x.float() * 2) - 1), w, b, AR)
+    y = ops.conv_in3(x[0].cuda(), w.cuda(), b.cuda(), 3, 2.0, -1.0)
+    assert rel_err(_ncthw(y), ref) < 3e-3
+    # 96 -> 3 head with planar NCTHW output and clamp
+    wh = _rand((3, 96, 3, 3, 3), 19, 0.05)
+    bh = _rand((3,), 20, 0.1)
+    refh = V.causal_conv3d(ref, wh, bh, AR).clamp(-1, 1)
+    vid = torch.empty(3, T, H, W, device="cuda", dtype=BF16)
+    ops.conv_cl(y, ops.pack_conv_weight(wh.cuda()), bh.cuda(), 3, (3, 3, 3), pad=(2, 1, 1), planar_out=vid, act=1)
+    assert rel_err(vid.float().cpu().unsqueeze(0), refh) < 3e-3
+
+
+def test_row_kernels(ops):
+    T, H, W, C = 2, 5, 7, 192
+    x = _rand((1, C, T, H, W), 21, 2.0)
+    g = _rand((C, 1, 1, 1), 22, 0.1) + 1
+    ref = V.silu(V.rms_norm(x.float(), g, AR), AR)
+    y = ops.rmsnorm_silu_cl(_cl(x), g.cuda())
+    assert rel_err(_ncthw(y), ref) < 3e-3
+    up = ops.upsample2x_cl(_cl(x))
+    refu = torch.nn.functional.interpolate(x[0].permute(1, 0, 2, 3).float(), scale_factor=2.0, mode="nearest-exact")
+    assert torch.equal(up.float().cpu().permute(0, 3, 1, 2), refu)
+    s = _rand((37, 24), 23, 3.0, torch.float32)
+    p = ops.softmax_rows(s.cuda(), 0.25)
+    assert rel_err(p.float().cpu(), torch.softmax(s * 0.25, -1)) < 3e-3
+    m = _rand((45, 70), 24)
+    assert torch.equal(ops.transpose_bf16(m.cuda()).cpu(), m.t().contiguous())
+    xa = _rand((1, 128, 3, 6, 10), 25, 2.0)
+    w, b = _rand((128,), 26, 0.1) + 1, _rand((128,), 27, 0.1)
+    refg = V._group_norm_swish(xa[0].permute(1, 0, 2, 3).float(), w, b, AR)            # [F, C, H, W]
+    yg = ops.groupnorm_swish_cl(_cl(xa), w.cuda(), b.cuda())
+    assert rel_err(yg.float().cpu().permute(0, 3, 1, 2), refg) < 4e-3
+
+
+def _vae():
+    from more4d_b200.vae import AutoencoderKLWan
+    m = AutoencoderKLWan(device="cuda")
+    m.load_state_dict(synth.vae_state_dict(seed=SEED), strict=True)
+    return m
+
+
+def test_vae_encode_decode(golden):
+    g = golden("vae")
+    sd = synth.vae_state_dict(seed=SEED)
+    x = synth._randn(SEED, "vae.x", (1, 3, 13, 32, 48), 0.5, "cpu", BF16)
+    z = synth._randn(SEED, "vae.z", (1, 16, 4, 4, 6), 1.0, "cpu", BF16)
+    m = _vae()
+    with torch.no_grad():
+        dist = m.encode(x.cuda())[0]
+        params = dist.parameters.float().cpu()
+        rec = m.decode(z.cuda()).sample.float().cpu()
+        p1 = m.encode(x[:, :, :1].cuda()).latent_dist.parameters.float().cpu()
+        r1 = m.decode(z[:, :, :1].cuda()).sample.float().cpu()
+    torch.cuda.synchronize()
+    assert params.shape == (1, 32, 4, 4, 6) and rec.shape == (1, 3, 13, 32, 48)
+    assert torch.equal(dist.mode().float().cpu(), params[:, :16])
+    pe, re_ = V.encode(x.float(), sd, emulate_bf16=True), V.decode(z.float(), sd, emulate_bf16=True)
+    errs = dict(enc_vs_emul=rel_err(params, pe), enc_vs_ref=rel_err(params, g["enc_params"]),
+                dec_vs_emul=rel_err(rec, re_), dec_vs_ref=rel_err(rec, g["dec"]),
+                enc1_vs_ref=rel_err(p1, g["enc_params_T1"]), dec1_vs_ref=rel_err(r1, g["dec_T1"]),
+                oracle_emul_vs_ref_enc=rel_err(pe, g["enc_params"]), oracle_emul_vs_ref_dec=rel_err(re_, g["dec"]))
+    print({k: f"{v:.3e}" for k, v in errs.items()})
+    for k in ("enc_vs_emul", "enc_vs_ref", "dec_vs_emul", "dec_vs_ref", "enc1_vs_ref", "dec1_vs_ref"):
+        assert errs[k] < 3e-2, (k, errs)
+
+
+def test_adaptors_and_roundtrip(golden):
+    from more4d_b200.vae import VAEDecoderadaptor, VAEEncoderadaptor, motion_vae_roundtrip
+    g = golden("vae")
+    tv = synth.trajectory_video(5, 32, 48, SEED)
+    esd, dsd = synth.adaptor_state_dict("encoder", SEED), synth.adaptor_state_dict("decoder", SEED)
+    ea, da = VAEEncoderadaptor(device="cuda"), VAEDecoderadaptor(device="cuda")
+    ea.load_state_dict(esd, strict=True)
+    da.load_state_dict(dsd, strict=True)
+    with torch.no_grad():
+        ye = ea(tv.cuda()).float().cpu()
+        yd = da(tv.cuda()).float().cpu()
+    errs = dict(enc_vs_ref=rel_err(ye, g["adaptor_enc"]), dec_vs_ref=rel_err(yd, g["adaptor_dec"]),
+                enc_vs_emul=rel_err(ye, V.encoder_adaptor(tv.float(), esd, True)),
+                dec_vs_emul=rel_err(yd, V.decoder_adaptor(tv.float(), dsd, True)))
+    print({k: f"{v:.3e}" for k, v in errs.items()})
+    assert errs["enc_vs_ref"] < 5e-3 and errs["enc_vs_emul"] < 5e-3
+    assert errs["dec_vs_ref"] < 3e-2 and errs["dec_vs_emul"] < 3e-2
+    # whole Motion-Sensitive round trip (infer_vae.py:276-281 with .mode())
+    vsd = synth.vae_state_dict(seed=SEED)
+    with torch.no_grad():
+        out, lat, rec = motion_vae_roundtrip(tv.cuda(), _vae(), ea, da)
+    ro, rl, rr = V.roundtrip(tv.float(), vsd, esd, dsd, emulate_bf16=True)
+    assert out.shape == tv.shape and lat.shape == (1, 16, 2, 4, 6)
+    e = dict(latent=rel_err(lat.float().cpu(), rl), video=rel_err(rec.float().cpu(), rr),
+             out=rel_err(out.float().cpu(), ro))
+    print({k: f"{v:.3e}" for k, v in e.items()})
+    assert e["latent"] < 3e-2 and e["video"] < 5e-2 and e["out"] < 8e-2
