@@ -201,12 +201,14 @@ def main():
     l0 = ops.launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.nvtx.range_push("m4d_timed")          # ncu --nvtx --nvtx-include "m4d_timed/"
     ev0.record()
     run(args.steps, lat, args.warmup)
     if world > 1:
         dist.all_gather(gathered, lat)
     ev1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     clocks = sampler.stop()
     timed = ops.stop_kernel_timing()
     launches = ops.launches() - l0
