@@ -161,7 +161,7 @@ def main():
 
     # ------------------------------------------------------------------ our arm (B200)
     import torch.distributed as dist
-    from more4d_b200 import ops, synth
+    from more4d_b200 import dist as mdist, ops, synth
     from more4d_b200.dit import WanTransformer4DModel
     from more4d_b200.pipeline import StraGDenoiser, synthetic_conditioning
 
@@ -180,7 +180,7 @@ def main():
                                                  text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
     lat = lat_host.to(dev)
     cond = cond_host.to(dev)
-    gathered = [torch.empty_like(lat) for _ in range(world)] if world > 1 else None
+    gathered = None
 
     def barrier():
         if world > 1:
@@ -205,7 +205,7 @@ def main():
     ev0.record()
     run(args.steps, lat, args.warmup)
     if world > 1:
-        dist.all_gather(gathered, lat)
+        gathered = mdist.gather_latents([lat], world)     # the north-star's one collective
     ev1.record()
     barrier()
     torch.cuda.nvtx.range_pop()

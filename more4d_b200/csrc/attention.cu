@@ -38,6 +38,75 @@ constexpr int A_THREADS = 384;
 constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024;
 
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
+constexpr int A_DEFAULT_VAR = 0;
+constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe (measured: 0 is fastest)
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// (d0, d1) = (a0, a1) * b + c     — one FFMA2
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1,
+                                     float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
+  asm("{ .reg .b64 ra, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rd, {%0, %1};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
+}
+// 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split with a round-down
+// magic add, degree-3 minimax polynomial for 2^frac (rel. error ~1e-4, far below the bf16
+// rounding of P), exponent re-inserted with an integer add.  Offloads part of the softmax's
+// exponentials from the 16/clk/SM MUFU, which is otherwise co-critical with the tensor pipe.
+__device__ __forceinline__ void ex2_emul2(float x0, float x1, float& r0, float& r1) {
+  const float kMagic = 12582912.0f;              // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t0) : "f"(x0), "f"(kMagic));
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t1) : "f"(x1), "f"(kMagic));
+  float b0 = t0, b1 = t1;
+  add2(b0, b1, -kMagic, -kMagic);                // floor(x)
+  float f0, f1;
+  fma2(f0, f1, b0, b1, -1.0f, -1.0f, x0, x1);    // frac = x - floor(x) in [0, 1)
+  float p0, p1;
+  fma2(p0, p1, f0, f1, 0.077119089663028717f, 0.077119089663028717f, 0.227564394474029541f,
+       0.227564394474029541f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.695146143436431885f, 0.695146143436431885f);
+  fma2(p0, p1, p0, p1, f0, f1, 1.0f, 1.0f);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// p = 2^(s*c + neg_mc) for 64 logits -> 32 packed bf16x2 registers; PP of every 8 pairs use the
+// polynomial path.  Row-sum partials are accumulated pairwise (FADD2).
+template <int PP, int Q0, int Q1>
+__device__ __forceinline__ void exp_pairs(const uint32_t* s, uint32_t* pk, float c, float neg_mc,
+                                          float& l0, float& l1) {
+#pragma unroll
+  for (int q = Q0; q < Q1; ++q) {
+    float x0, x1, p0, p1;
+    fma2(x0, x1, __uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1]), c, c, neg_mc, neg_mc);
+    if ((q & 7) >= 8 - PP) {
+      ex2_emul2(x0, x1, p0, p1);
+    } else {
+      p0 = fast_exp2(x0);
+      p1 = fast_exp2(x1);
+    }
+    add2(l0, l1, p0, p1);
+    pk[q] = pack_bf16(p0, p1);
+  }
+}
 
 struct AttnParams {
   bf16* out;
@@ -49,6 +118,11 @@ struct AttnParams {
   int flags;                              // debug variants, see m4d_set_debug_flags
 };
 
+// VAR bits select micro-variants measured on the B200 (tools/gpu_probe.py attn_sweep):
+//   1: one mbarrier arrival per softmax warp instead of per thread
+//   2: second half of the S tile is loaded from TMEM while the first half is max-reduced
+//   4: second-half exponentials start before waiting for the first P store to drain
+template <int PP, int VAR>
 __global__ void __launch_bounds__(A_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -65,8 +139,8 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* v_full = k_empty + A_KS;    // A_VS
   uint64_t* v_empty = v_full + A_VS;    // A_VS
   uint64_t* s_full = v_empty + A_VS;    // 2
-  uint64_t* p_ready = s_full + 2;       // 2
-  uint64_t* o_final = p_ready + 2;      // 2
+  uint64_t* p_ready = s_full + 2;       // 2 tiles x 2 key-halves: [t * 2 + half]
+  uint64_t* o_final = p_ready + 4;      // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -98,7 +172,8 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_ready[t], 128);
+      mbar_init(&p_ready[2 * t], (VAR & 1) ? 4 : 128);
+      mbar_init(&p_ready[2 * t + 1], (VAR & 1) ? 4 : 128);
       mbar_init(&o_final[t], 1);
     }
     fence_mbar_init();
@@ -138,8 +213,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
       // V descriptor strides: 64-wide d chunks are 16 KB apart, 8-key groups 1 KB apart.
-      const uint32_t v_lbo = (p.flags & 1) ? 1024 : A_HALF_BYTES;
-      const uint32_t v_sbo = (p.flags & 1) ? A_HALF_BYTES : 1024;
+      const uint32_t v_lbo = A_HALF_BYTES, v_sbo = 1024;
 
       auto issue_qk = [&](int t, int sk) {
 #pragma unroll
@@ -150,9 +224,12 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_ss(tS[t], ad, bd, idesc_qk, kk != 0);
         }
       };
-      auto issue_pv = [&](int t, int sv, bool first) {
+      // O_t += P_t[:, half*64 .. +64] V[half*64 .. +64, :]   (P is split so the first half of
+      // the PV MMAs overlaps the exponentials of the second half)
+      auto issue_pv = [&](int t, int sv, int half, bool first) {
 #pragma unroll
-        for (int kk = 0; kk < A_BKV / 16; ++kk) {
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int kk = half * 4 + k4;
           const uint64_t bd = umma_smem_desc(v_addr + sv * A_TILE_BYTES + kk * 2048, v_lbo, v_sbo);
           umma_ts(tO[t], tS[t] + kk * 8, bd, idesc_pv, !(first && kk == 0));
         }
@@ -173,7 +250,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&v_full[sv], (j / A_VS) & 1);
         mbar_wait(&p_ready[0], j & 1);
         tc_fence_after();
-        issue_pv(0, sv, j == 0);
+        issue_pv(0, sv, 0, j == 0);
+        mbar_wait(&p_ready[1], j & 1);
+        tc_fence_after();
+        issue_pv(0, sv, 1, j == 0);
         if (last) {
           umma_commit(&o_final[0]);
         } else {
@@ -182,9 +262,12 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           issue_qk(0, sk);
           umma_commit(&s_full[0]);
         }
-        mbar_wait(&p_ready[1], j & 1);
+        mbar_wait(&p_ready[2], j & 1);
         tc_fence_after();
-        issue_pv(1, sv, j == 0);
+        issue_pv(1, sv, 0, j == 0);
+        mbar_wait(&p_ready[3], j & 1);
+        tc_fence_after();
+        issue_pv(1, sv, 1, j == 0);
         umma_commit(&v_empty[sv]);
         if (last) {
           umma_commit(&o_final[1]);
@@ -214,24 +297,49 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t s[128];
       tmem_ld32(tS + 0, s + 0);
       tmem_ld32(tS + 32, s + 32);
-      tmem_ld32(tS + 64, s + 64);
-      tmem_ld32(tS + 96, s + 96);
+      if (!(VAR & 2)) {
+        tmem_ld32(tS + 64, s + 64);
+        tmem_ld32(tS + 96, s + 96);
+      }
       tmem_ld_wait();
+      reg_fence32(s + 0);
+      reg_fence32(s + 32);
+      if (VAR & 2) {
+        tmem_ld32(tS + 64, s + 64);          // in flight while the first 64 logits are reduced
+        tmem_ld32(tS + 96, s + 96);
+      }
 
       const int valid = kv_len - j * A_BKV;        // keys of this tile that exist
-      if (valid < A_BKV) {
+      if (valid < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < 64; ++i)
           if (i >= valid) s[i] = 0xFF800000u;      // -inf
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
       float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int i = 4; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      for (int i = 4; i < 60; i += 8) {        // FMNMX3: two logits per instruction
+        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+      }
+      mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
+      mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
+      if (VAR & 2) tmem_ld_wait();
+      reg_fence32(s + 64);
+      reg_fence32(s + 96);
+      if (valid < A_BKV) {
+#pragma unroll
+        for (int i = 64; i < 128; ++i)
+          if (i >= valid) s[i] = 0xFF800000u;
+      }
+#pragma unroll
+      for (int i = 64; i < 128; i += 8) {
+        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       if (j == 0) {
@@ -256,29 +364,34 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       const float neg_mc = -m_used * c;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[h * 64 + 2 * i + 0]), c, neg_mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[h * 64 + 2 * i + 1]), c, neg_mc));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(s[h * 64 + 2 * i + 2]), c, neg_mc));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(s[h * 64 + 2 * i + 3]), c, neg_mc));
-          l0 += p0;
-          l1 += p1;
-          l2 += p2;
-          l3 += p3;
-          pk[i] = (p.flags & 2) ? pack_bf16(p1, p0) : pack_bf16(p0, p1);
-          pk[i + 1] = (p.flags & 2) ? pack_bf16(p3, p2) : pack_bf16(p2, p3);
+      float l0 = 0.f, l1 = 0.f;
+      {
+        uint32_t pa[32], pb[32];
+        exp_pairs<PP, 0, 32>(s, pa, c, neg_mc, l0, l1);
+        tmem_st32(tS, pa);
+        // (VAR 4) keep the MUFU busy with the second half while the first P store drains
+        if (VAR & 4) exp_pairs<PP, 0, 8>(s + 64, pb, c, neg_mc, l0, l1);
+        tmem_st_wait();
+        tc_fence_before();
+        if (VAR & 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[2 * t]);
+        } else {
+          mbar_arrive(&p_ready[2 * t]);
         }
-        tmem_st32(tS + h * 32, pk);
+        if (VAR & 4) exp_pairs<PP, 8, 32>(s + 64, pb, c, neg_mc, l0, l1);
+        else exp_pairs<PP, 0, 32>(s + 64, pb, c, neg_mc, l0, l1);
+        tmem_st32(tS + 32, pb);
+        tmem_st_wait();
+        tc_fence_before();
+        if (VAR & 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[2 * t + 1]);
+        } else {
+          mbar_arrive(&p_ready[2 * t + 1]);
+        }
       }
-      l_sum += (l0 + l1) + (l2 + l3);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[t]);
+      l_sum += l0 + l1;
     }
 
     // ---- epilogue: O / l -> bf16 -> global
@@ -361,14 +474,31 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
   if ((rc = mk(&tmK, k, Lk, kv_stride_b, kv_stride_l)) != M4D_OK) return rc;
   if ((rc = mk(&tmV, v, Lk, kv_stride_b, kv_stride_l)) != M4D_OK) return rc;
 
-  static bool configured = false;
-  if (!configured) {
-    rc = cuda_ok(cudaFuncSetAttribute(attn_fwd_d128_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM_BYTES),
-                 "cudaFuncSetAttribute(attention)");
-    if (rc != M4D_OK) return rc;
-    configured = true;
+  // debug flags: 0x100 | (PP << 4) | VAR selects a measured variant; default = fastest measured
+  int pp = A_DEFAULT_PP, var = A_DEFAULT_VAR;
+  if (g_debug_flags & 0x100) {
+    pp = (g_debug_flags >> 4) & 0xF;
+    var = g_debug_flags & 0x7;
   }
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = nullptr;
+  if (pp == 0) {
+    switch (var) {
+      case 0: kern = attn_fwd_d128_kernel<0, 0>; break;
+      case 1: kern = attn_fwd_d128_kernel<0, 1>; break;
+      case 2: kern = attn_fwd_d128_kernel<0, 2>; break;
+      case 3: kern = attn_fwd_d128_kernel<0, 3>; break;
+      case 4: kern = attn_fwd_d128_kernel<0, 4>; break;
+      case 5: kern = attn_fwd_d128_kernel<0, 5>; break;
+      case 6: kern = attn_fwd_d128_kernel<0, 6>; break;
+      case 7: kern = attn_fwd_d128_kernel<0, 7>; break;
+    }
+  } else if (pp == 2) {
+    kern = (var & 1) ? attn_fwd_d128_kernel<2, 7> : attn_fwd_d128_kernel<2, 0>;
+  }
+  if (kern == nullptr) return M4D_ERR_UNSUPPORTED;
+  rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM_BYTES),
+               "cudaFuncSetAttribute(attention)");
+  if (rc != M4D_OK) return rc;
   AttnParams p;
   p.out = static_cast<bf16*>(out);
   p.out_stride_b = out_stride_b;
@@ -382,7 +512,7 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
   p.accumulate = accumulate;
   p.flags = g_debug_flags;
   dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
-  attn_fwd_d128_kernel<<<grid, A_THREADS, A_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, A_THREADS, A_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   M4D_CHECK_LAUNCH("attn_fwd_d128_kernel");
   return M4D_OK;
 }

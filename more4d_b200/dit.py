@@ -447,6 +447,19 @@ class WanTransformer4DModel(nn.Module):
     def disable_cfg_skip(self):
         self.cfg_skip_ratio, self.current_steps, self.num_inference_steps = None, 0, None
 
+    # TeaCache hooks of the reference (t4d:961-978)
+    def enable_teacache(self, coefficients, num_steps: int, rel_l1_thresh: float,
+                        num_skip_start_steps: int = 0, offload: bool = True):
+        from .cache_utils import TeaCache
+        self.teacache = TeaCache(coefficients, num_steps, rel_l1_thresh=rel_l1_thresh,
+                                 num_skip_start_steps=num_skip_start_steps, offload=offload)
+
+    def share_teacache(self, transformer=None):
+        self.teacache = transformer.teacache
+
+    def disable_teacache(self):
+        self.teacache = None
+
     # ---------------------------------------------------------------------------------
     def embed_time(self, t: Tensor):
         """e [B, C], e0 [B, 6, C] in fp32 (t4d:1160-1171)."""
@@ -486,8 +499,6 @@ class WanTransformer4DModel(nn.Module):
         if first_frame is not None:
             raise NotImplementedError("first_frame requires the OmniMAE trunk (out of scope); "
                                       "pass guidance_features instead")
-        if self.teacache is not None:
-            raise NotImplementedError("TeaCache is not wired into the B200 path yet")
         # @cfg_skip() wrapper semantics (cfg_optimization.py:5-39)
         bs = len(x)
         skip = (bs >= 2 and self.cfg_skip_ratio is not None and
@@ -498,12 +509,12 @@ class WanTransformer4DModel(nn.Module):
             clip_fea = None if clip_fea is None else clip_fea[h:]
             y = None if y is None else y[h:]
             full_ref = None if full_ref is None else full_ref[h:]
-        out = self._forward(x, t, context, seq_len, clip_fea, y, full_ref, guidance_features)
+        out = self._forward(x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag)
         if skip:
             out = torch.cat([out, out], dim=0)
         return out
 
-    def _forward(self, x, t, context, seq_len, clip_fea, y, full_ref, guidance_features):
+    def _forward(self, x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag=True):
         dev = self.patch_embedding.weight.device
         if isinstance(x, (list, tuple)):
             x = torch.stack(list(x))
@@ -542,8 +553,27 @@ class WanTransformer4DModel(nn.Module):
         ctx = self.embed_context([c.to(device=dev, dtype=BF16) for c in context], clip_fea)
         seq_lens = torch.full((B,), n_tok, device=dev, dtype=torch.int32)
         grid_sizes = torch.tensor([grid] * B, device=dev, dtype=torch.int32)
-        for blk in self.blocks:
-            xs = blk(xs, e0, seq_lens, grid_sizes, self.freqs, ctx, None, BF16, t,
-                     dino_features=guidance_features, use_cls_token=self.use_cls_token)
+        run_blocks = True
+        tc = self.teacache
+        if tc is not None:                                         # t4d:1200-1270
+            run_blocks = tc.decide(e0, cond_flag)
+            if not run_blocks:
+                prev = tc.previous_residual_cond if cond_flag else tc.previous_residual_uncond
+                xs = xs + prev.to(xs.device)[-xs.size(0):]         # cache hit: block stack skipped
+            else:
+                ori = xs.clone().cpu() if tc.offload else xs.clone()
+        if run_blocks:
+            for blk in self.blocks:
+                xs = blk(xs, e0, seq_lens, grid_sizes, self.freqs, ctx, None, BF16, t,
+                         dino_features=guidance_features, use_cls_token=self.use_cls_token)
+            if tc is not None:
+                res = (xs.cpu() - ori) if tc.offload else (xs - ori)
+                if cond_flag:
+                    tc.previous_residual_cond = res
+                else:
+                    tc.previous_residual_uncond = res
         tok = self.head(xs, e)                                     # [B, L, 64] bf16
-        return ops.unpatchify(tok, ref_len, self.out_dim, T, H, W)
+        out = ops.unpatchify(tok, ref_len, self.out_dim, T, H, W)
+        if tc is not None:
+            tc.step_done(cond_flag)
+        return out

@@ -117,3 +117,28 @@ def test_model_call_surface_list_inputs_and_cfg_skip():
         assert torch.equal(y3[0], y3[1]) and torch.equal(y3[1], y1[1])
     with pytest.raises(RuntimeError):
         model(x=inp["x"].cuda(), y=inp["y"].cuda(), **kw)          # grad enabled -> refuse
+
+
+def test_teacache_skips_block_stack():
+    """TeaCache hooks (t4d:1200-1270): with a huge threshold the second step re-uses the cached
+    block residual, so it launches far fewer kernels and still returns a finite prediction."""
+    from more4d_b200 import ops
+    from more4d_b200.dit import WanTransformer4DModel
+    cfg, grid, seed = WAN_TINY, (2, 2, 3), 9
+    sd = synth.dit_state_dict(cfg, seed)
+    inp = synth.dit_inputs(cfg, grid, 2, seed)
+    model = WanTransformer4DModel.from_config(cfg, device="cuda")
+    model.load_state_dict(sd, strict=True)
+    model.enable_teacache([0.0, 0.0, 0.0, 1.0, 0.0], num_steps=3, rel_l1_thresh=1e9, offload=False)
+    kw = dict(context=[c.cuda() for c in inp["context"]], seq_len=inp["seq_len"],
+              clip_fea=inp["clip_fea"].cuda(), full_ref=inp["full_ref"].cuda())
+    with torch.no_grad():
+        n0 = ops.launches()
+        y1 = model(x=inp["x"].cuda(), y=inp["y"].cuda(), t=torch.tensor([500.0, 500.0]).cuda(), **kw)
+        n1 = ops.launches()
+        y2 = model(x=inp["x"].cuda(), y=inp["y"].cuda(), t=torch.tensor([480.0, 480.0]).cuda(), **kw)
+        n2 = ops.launches()
+    assert model.teacache.cnt == 2 and model.teacache.should_calc is False
+    assert (n2 - n1) < (n1 - n0) // 2
+    assert torch.isfinite(y2.float()).all() and y2.shape == y1.shape
+    model.disable_teacache()

@@ -105,6 +105,33 @@ def attn():
                       f" rel vs ours {rel(out.float(), o2.transpose(1, 2).float()):.3e}", flush=True)
 
 
+def attn_sweep():
+    """Polynomial-exp2 share sweep (debug flags 0x10 | PP) at the bench shape + parity."""
+    ar = O.Arith(True)
+    q, k, v = rnd((1, 300, 2, 128), 1), rnd((1, 300, 2, 128), 2), rnd((1, 300, 2, 128), 3)
+    ref = O.attention(q, k, v, None, ar)
+    B, L, N = 2, 50400, 40
+    Q, K, V = (torch.randn(B, L, N, 128, device="cuda", dtype=BF16) for _ in range(3))
+    out = torch.empty_like(Q)
+    fl = 4.0 * B * N * L * L * 128
+    for pp, var in [(0, v) for v in range(8)] + [(2, 0), (2, 1)] + [(0, v) for v in range(8)]:
+        _lib.lib().m4d_set_debug_flags(0x100 | (pp << 4) | var)
+        o = ops.attention(q.cuda(), k.cuda(), v.cuda())
+        e = rel(o.float().cpu(), ref)
+        ops.attention(Q, K, V, out=out)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+            s_.record()
+            ops.attention(Q, K, V, out=out)
+            e_.record(); torch.cuda.synchronize()
+            ts.append(s_.elapsed_time(e_))
+        ms = min(ts)
+        print(f"PP={pp} VAR={var}: parity rel={e:.3e}  {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s (all: {[round(t,1) for t in ts]})", flush=True)
+    _lib.lib().m4d_set_debug_flags(0)
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    {"gemm": gemm, "attn": attn}[sys.argv[1]]()
+    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep}[sys.argv[1]]()
