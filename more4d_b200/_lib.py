@@ -75,6 +75,9 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        flags = os.environ.get("M4D_DEBUG_FLAGS")       # development only: kernel variant selection
+        if flags:
+            l.m4d_set_debug_flags(int(flags, 0))
         _lib = l
     return _lib
 

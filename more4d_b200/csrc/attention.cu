@@ -39,6 +39,7 @@ constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024;
 
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
 constexpr int A_DEFAULT_VAR = 0;
+constexpr int A_DEFAULT_K64 = 0;              // 1: use the double-buffered 64-key-step kernel
 constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe (measured: 0 is fastest)
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -118,10 +119,12 @@ struct AttnParams {
   int flags;                              // debug variants, see m4d_set_debug_flags
 };
 
-// VAR bits select micro-variants measured on the B200 (tools/gpu_probe.py attn_sweep):
-//   1: one mbarrier arrival per softmax warp instead of per thread
-//   2: second half of the S tile is loaded from TMEM while the first half is max-reduced
-//   4: second-half exponentials start before waiting for the first P store to drain
+// VAR = 0: P is handed to the tensor pipe in two 64-key halves; VAR = 1: in four 32-key
+// quarters (finer PV / exp overlap, more barrier traffic).  Measured variants that did NOT
+// help on the B200 and were removed again: one mbarrier arrival per warp instead of per thread
+// (-4 %), loading the second half of S while max-reducing the first (-1 %), polynomial exp2 on
+// the FMA pipe for 12-50 % of the logits (PP > 0: -4 .. -11 %, the softmax is latency-, not
+// MUFU-bound), and the double-buffered 64-key-step kernel below (-25 %).
 template <int PP, int VAR>
 __global__ void __launch_bounds__(A_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -139,8 +142,8 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* v_full = k_empty + A_KS;    // A_VS
   uint64_t* v_empty = v_full + A_VS;    // A_VS
   uint64_t* s_full = v_empty + A_VS;    // 2
-  uint64_t* p_ready = s_full + 2;       // 2 tiles x 2 key-halves: [t * 2 + half]
-  uint64_t* o_final = p_ready + 4;      // 2
+  uint64_t* p_ready = s_full + 2;       // 2 tiles x up to 4 key-slices: [t * 4 + slice]
+  uint64_t* o_final = p_ready + 8;      // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -172,8 +175,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_ready[2 * t], (VAR & 1) ? 4 : 128);
-      mbar_init(&p_ready[2 * t + 1], (VAR & 1) ? 4 : 128);
+      for (int i = 0; i < 4; ++i) mbar_init(&p_ready[4 * t + i], 128);
       mbar_init(&o_final[t], 1);
     }
     fence_mbar_init();
@@ -224,14 +226,20 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_ss(tS[t], ad, bd, idesc_qk, kk != 0);
         }
       };
-      // O_t += P_t[:, half*64 .. +64] V[half*64 .. +64, :]   (P is split so the first half of
-      // the PV MMAs overlaps the exponentials of the second half)
-      auto issue_pv = [&](int t, int sv, int half, bool first) {
+      // O_t += P_t[:, slice] V[slice, :] — P arrives in NS key-slices so the first PV MMAs
+      // overlap the exponentials of the later slices
+      constexpr int NS = (VAR == 1) ? 4 : (VAR == 2 ? 1 : 2);
+      auto issue_pv_tile = [&](int t, int sv, int j) {
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const int kk = half * 4 + k4;
-          const uint64_t bd = umma_smem_desc(v_addr + sv * A_TILE_BYTES + kk * 2048, v_lbo, v_sbo);
-          umma_ts(tO[t], tS[t] + kk * 8, bd, idesc_pv, !(first && kk == 0));
+        for (int sl = 0; sl < NS; ++sl) {
+          mbar_wait(&p_ready[4 * t + sl], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 8 / NS; ++k4) {
+            const int kk = sl * (8 / NS) + k4;
+            const uint64_t bd = umma_smem_desc(v_addr + sv * A_TILE_BYTES + kk * 2048, v_lbo, v_sbo);
+            umma_ts(tO[t], tS[t] + kk * 8, bd, idesc_pv, !(j == 0 && kk == 0));
+          }
         }
       };
 
@@ -248,12 +256,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const bool last = (j + 1 == n_kv);
         const int sk = (j + 1) % A_KS;
         mbar_wait(&v_full[sv], (j / A_VS) & 1);
-        mbar_wait(&p_ready[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, sv, 0, j == 0);
-        mbar_wait(&p_ready[1], j & 1);
-        tc_fence_after();
-        issue_pv(0, sv, 1, j == 0);
+        issue_pv_tile(0, sv, j);
         if (last) {
           umma_commit(&o_final[0]);
         } else {
@@ -262,12 +265,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           issue_qk(0, sk);
           umma_commit(&s_full[0]);
         }
-        mbar_wait(&p_ready[2], j & 1);
-        tc_fence_after();
-        issue_pv(1, sv, 0, j == 0);
-        mbar_wait(&p_ready[3], j & 1);
-        tc_fence_after();
-        issue_pv(1, sv, 1, j == 0);
+        issue_pv_tile(1, sv, j);
         umma_commit(&v_empty[sv]);
         if (last) {
           umma_commit(&o_final[1]);
@@ -297,17 +295,11 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t s[128];
       tmem_ld32(tS + 0, s + 0);
       tmem_ld32(tS + 32, s + 32);
-      if (!(VAR & 2)) {
-        tmem_ld32(tS + 64, s + 64);
-        tmem_ld32(tS + 96, s + 96);
-      }
+      tmem_ld32(tS + 64, s + 64);
+      tmem_ld32(tS + 96, s + 96);
       tmem_ld_wait();
       reg_fence32(s + 0);
       reg_fence32(s + 32);
-      if (VAR & 2) {
-        tmem_ld32(tS + 64, s + 64);          // in flight while the first 64 logits are reduced
-        tmem_ld32(tS + 96, s + 96);
-      }
 
       const int valid = kv_len - j * A_BKV;        // keys of this tile that exist
       if (valid < 64) {
@@ -326,7 +318,6 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
       mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
-      if (VAR & 2) tmem_ld_wait();
       reg_fence32(s + 64);
       reg_fence32(s + 96);
       if (valid < A_BKV) {
@@ -365,36 +356,330 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       const float neg_mc = -m_used * c;
       float l0 = 0.f, l1 = 0.f;
-      {
+      if (VAR == 1) {
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          uint32_t pq[16];
+          exp_pairs<PP, 0, 16>(s + sl * 32, pq, c, neg_mc, l0, l1);
+          tmem_st16(tS + sl * 16, pq);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_ready[4 * t + sl]);
+        }
+      } else if (VAR == 2) {
         uint32_t pa[32], pb[32];
         exp_pairs<PP, 0, 32>(s, pa, c, neg_mc, l0, l1);
         tmem_st32(tS, pa);
-        // (VAR 4) keep the MUFU busy with the second half while the first P store drains
-        if (VAR & 4) exp_pairs<PP, 0, 8>(s + 64, pb, c, neg_mc, l0, l1);
-        tmem_st_wait();
-        tc_fence_before();
-        if (VAR & 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_ready[2 * t]);
-        } else {
-          mbar_arrive(&p_ready[2 * t]);
-        }
-        if (VAR & 4) exp_pairs<PP, 8, 32>(s + 64, pb, c, neg_mc, l0, l1);
-        else exp_pairs<PP, 0, 32>(s + 64, pb, c, neg_mc, l0, l1);
+        exp_pairs<PP, 0, 32>(s + 64, pb, c, neg_mc, l0, l1);
         tmem_st32(tS + 32, pb);
         tmem_st_wait();
         tc_fence_before();
-        if (VAR & 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_ready[2 * t + 1]);
-        } else {
-          mbar_arrive(&p_ready[2 * t + 1]);
+        mbar_arrive(&p_ready[4 * t]);
+      } else {
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          uint32_t ph[32];
+          exp_pairs<PP, 0, 32>(s + sl * 64, ph, c, neg_mc, l0, l1);
+          tmem_st32(tS + sl * 32, ph);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_ready[4 * t + sl]);
         }
       }
       l_sum += l0 + l1;
     }
 
     // ---- epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_final[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
+    const bool row_ok = q_row < p.Lq;
+    bf16* orow = p.out + static_cast<long long>(b) * p.out_stride_b +
+                 static_cast<long long>(q_row) * p.out_stride_l + head * A_D;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tO + cc * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
+          if (p.accumulate) {
+            const uint4 prev = *dst;
+            const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
+              v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+          }
+          uint4 ov;
+          ov.x = pack_bf16(v[0], v[1]);
+          ov.y = pack_bf16(v[2], v[3]);
+          ov.z = pack_bf16(v[4], v[5]);
+          ov.w = pack_bf16(v[6], v[7]);
+          *dst = ov;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc<512>(tmem_base);
+}
+
+
+// =======================================================================================
+// Variant "k64": 64-key steps with DOUBLE-BUFFERED S per query tile.
+//
+// In the kernel above S_t(j+1) cannot be produced before P_t(j) has been consumed (P aliases S
+// and TMEM is full: S0|S1|O0|O1), so each query tile runs the serial chain
+// softmax -> PV -> QK -> softmax and the tensor pipe idles while a tile is in its softmax.
+// Here a step covers 64 keys, so S_t fits twice in the same 128 columns (S[t][0] | S[t][1]):
+// QK_t(j+1) is issued BEFORE PV_t(j) and lands in the other buffer while softmax_t(j) is still
+// running — the softmax warpgroups never wait for the tensor pipe and vice versa.  Costs: the
+// N=64 QK MMAs re-read the 4 KB Q slice per 64 keys (shared-memory bound, ~1.5x their ideal
+// time) and barrier traffic doubles.  O-rescale needs PV_t(j-1) to have finished, which is no
+// longer implied by "S_t(j) ready": a pv_done barrier is waited on only when a rescale happens.
+// TMEM columns: S[t][u] at (2t+u)*64, P[t][u] aliases its first 32 columns, O_t at 256 + 128 t.
+// =======================================================================================
+constexpr int B_BKV = 64;
+constexpr int B_KS = 4, B_VS = 4;
+constexpr int B_KV_TILE = B_BKV * 128 * 2;     // 16 KB = two [64 x 64] SW128 halves of 8 KB
+constexpr int B_KV_HALF = B_BKV * 64 * 2;
+constexpr int B_SMEM_BYTES = A_NQ * A_TILE_BYTES + (B_KS + B_VS) * B_KV_TILE + 256 + 1024;
+
+__global__ void __launch_bounds__(A_THREADS, 1)
+attn_fwd_d128_k64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + A_NQ * A_TILE_BYTES;
+  uint8_t* sV = sK + B_KS * B_KV_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + B_VS * B_KV_TILE);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* k_full = q_full + 1;         // B_KS
+  uint64_t* k_empty = k_full + B_KS;     // B_KS
+  uint64_t* v_full = k_empty + B_KS;     // B_VS
+  uint64_t* v_empty = v_full + B_VS;     // B_VS
+  uint64_t* s_full = v_empty + B_VS;     // [t*2 + u]
+  uint64_t* p_ready = s_full + 4;        // [t*2 + u]
+  uint64_t* pv_done = p_ready + 4;       // [t]
+  uint64_t* o_final = pv_done + 2;       // [t]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+
+  int kv_len = p.Lk;
+  if (p.k_lens != nullptr) {
+    int kl = p.k_lens[b];
+    kv_len = kl < kv_len ? kl : kv_len;
+  }
+  if (kv_len < 1) kv_len = 1;
+  const int n_kv = (kv_len + B_BKV - 1) / B_BKV;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 9 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < B_KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < B_VS; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&pv_done[t], 1);
+      mbar_init(&o_final[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 10) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    reg_dec<80>();
+    if (warp == 8 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
+      for (int t = 0; t < A_NQ; ++t)
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sQ + t * A_TILE_BYTES + h * A_HALF_BYTES, &tmQ, q_full, h * 64, head,
+                      q_blk * (A_NQ * A_BQ) + t * A_BQ, b);
+      auto load_k = [&](int j) {
+        const int sk = j % B_KS;
+        mbar_wait(&k_empty[sk], ((j / B_KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[sk], B_KV_TILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sK + sk * B_KV_TILE + h * B_KV_HALF, &tmK, &k_full[sk], h * 64, head, j * B_BKV, b);
+      };
+      auto load_v = [&](int j) {
+        const int sv = j % B_VS;
+        mbar_wait(&v_empty[sv], ((j / B_VS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], B_KV_TILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sV + sv * B_KV_TILE + h * B_KV_HALF, &tmV, &v_full[sv], h * 64, head, j * B_BKV, b);
+      };
+      load_k(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) load_k(j + 1);
+        load_v(j);
+      }
+    } else if (warp == 9 && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      auto issue_qk = [&](int t, int sk, int u) {
+        const uint32_t d = tmem_base + (t * 2 + u) * 64;
+#pragma unroll
+        for (int kk = 0; kk < A_D / 16; ++kk) {
+          const uint64_t ad = umma_smem_desc(
+              q_addr + t * A_TILE_BYTES + (kk >> 2) * A_HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_smem_desc(
+              k_addr + sk * B_KV_TILE + (kk >> 2) * B_KV_HALF + (kk & 3) * 32, 16, 1024);
+          umma_ss(d, ad, bd, idesc_qk, kk != 0);
+        }
+      };
+      auto issue_pv = [&](int t, int sv, int u, bool first) {
+        const uint32_t a = tmem_base + (t * 2 + u) * 64;
+        const uint32_t d = tmem_base + 256 + t * 128;
+#pragma unroll
+        for (int kk = 0; kk < B_BKV / 16; ++kk) {
+          const uint64_t bd = umma_smem_desc(v_addr + sv * B_KV_TILE + kk * 2048, B_KV_HALF, 1024);
+          umma_ts(d, a + kk * 8, bd, idesc_pv, !(first && kk == 0));
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0, 0);
+      umma_commit(&s_full[0]);
+      issue_qk(1, 0, 0);
+      umma_commit(&s_full[2]);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int u = j & 1;
+        const bool last = (j + 1 == n_kv);
+        if (!last) {
+          const int sk = (j + 1) % B_KS;
+          mbar_wait(&k_full[sk], ((j + 1) / B_KS) & 1);
+          tc_fence_after();
+          issue_qk(0, sk, u ^ 1);
+          umma_commit(&s_full[0 + (u ^ 1)]);
+          issue_qk(1, sk, u ^ 1);
+          umma_commit(&s_full[2 + (u ^ 1)]);
+          umma_commit(&k_empty[sk]);
+        }
+        const int sv = j % B_VS;
+        mbar_wait(&v_full[sv], (j / B_VS) & 1);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_ready[t * 2 + u], (j >> 1) & 1);
+          tc_fence_after();
+          issue_pv(t, sv, u, j == 0);
+          umma_commit(&pv_done[t]);
+          if (last) umma_commit(&o_final[t]);
+        }
+        umma_commit(&v_empty[sv]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    reg_inc<208>();
+    const int t = warp >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
+    const float c = p.scale_log2;
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int u = j & 1;
+      const uint32_t tS = tmem_base + lane_base + (t * 2 + u) * 64;
+      mbar_wait(&s_full[t * 2 + u], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      tmem_ld32(tS + 0, s + 0);
+      tmem_ld32(tS + 32, s + 32);
+      tmem_ld_wait();
+      reg_fence32(s + 0);
+      reg_fence32(s + 32);
+      const int valid = kv_len - j * B_BKV;
+      if (valid < B_BKV) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = 0xFF800000u;
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int i = 4; i < 60; i += 8) {
+        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+      }
+      mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
+      mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const float m_new = fmaxf(m_used, mx);
+        const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);       // PV_t(j-1) must have landed in O_t
+          tc_fence_after();
+          const float f = fast_exp2((m_used - m_new) * c);
+          m_used = m_new;
+          l_sum *= f;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tO + cc * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float neg_mc = -m_used * c;
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t pk[32];
+      exp_pairs<0, 0, 32>(s, pk, c, neg_mc, l0, l1);
+      tmem_st32(tS, pk);
+      l_sum += l0 + l1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[t * 2 + u]);
+    }
+
     mbar_wait(&o_final[t], 0);
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
@@ -460,9 +745,10 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
                   aligned16(out),
               M4D_ERR_ALIGN);
 
+  const bool k64 = (g_debug_flags & 0x200) ? ((g_debug_flags & 0x400) != 0) : (A_DEFAULT_K64 != 0);
   CUtensorMap tmQ, tmK, tmV;
-  const uint32_t box[4] = {64, 1, 128, 1};
-  auto mk = [&](CUtensorMap* m, const void* base, int L, long long sb, long long sl) {
+  auto mk = [&](CUtensorMap* m, const void* base, int L, long long sb, long long sl, uint32_t rows) {
+    const uint32_t box[4] = {64, 1, rows, 1};
     uint64_t dims[4] = {static_cast<uint64_t>(A_D), static_cast<uint64_t>(heads),
                         static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
     uint64_t str[3] = {static_cast<uint64_t>(A_D) * 2, static_cast<uint64_t>(sl) * 2,
@@ -470,9 +756,10 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
     return make_tmap_bf16(m, base, 4, dims, str, box);
   };
   int rc;
-  if ((rc = mk(&tmQ, q, Lq, q_stride_b, q_stride_l)) != M4D_OK) return rc;
-  if ((rc = mk(&tmK, k, Lk, kv_stride_b, kv_stride_l)) != M4D_OK) return rc;
-  if ((rc = mk(&tmV, v, Lk, kv_stride_b, kv_stride_l)) != M4D_OK) return rc;
+  const uint32_t kv_rows = k64 ? B_BKV : A_BKV;
+  if ((rc = mk(&tmQ, q, Lq, q_stride_b, q_stride_l, A_BQ)) != M4D_OK) return rc;
+  if ((rc = mk(&tmK, k, Lk, kv_stride_b, kv_stride_l, kv_rows)) != M4D_OK) return rc;
+  if ((rc = mk(&tmV, v, Lk, kv_stride_b, kv_stride_l, kv_rows)) != M4D_OK) return rc;
 
   // debug flags: 0x100 | (PP << 4) | VAR selects a measured variant; default = fastest measured
   int pp = A_DEFAULT_PP, var = A_DEFAULT_VAR;
@@ -481,22 +768,15 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
     var = g_debug_flags & 0x7;
   }
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = nullptr;
-  if (pp == 0) {
-    switch (var) {
-      case 0: kern = attn_fwd_d128_kernel<0, 0>; break;
-      case 1: kern = attn_fwd_d128_kernel<0, 1>; break;
-      case 2: kern = attn_fwd_d128_kernel<0, 2>; break;
-      case 3: kern = attn_fwd_d128_kernel<0, 3>; break;
-      case 4: kern = attn_fwd_d128_kernel<0, 4>; break;
-      case 5: kern = attn_fwd_d128_kernel<0, 5>; break;
-      case 6: kern = attn_fwd_d128_kernel<0, 6>; break;
-      case 7: kern = attn_fwd_d128_kernel<0, 7>; break;
-    }
-  } else if (pp == 2) {
-    kern = (var & 1) ? attn_fwd_d128_kernel<2, 7> : attn_fwd_d128_kernel<2, 0>;
+  if (pp == 0) kern = var == 1 ? attn_fwd_d128_kernel<0, 1> : (var == 2 ? attn_fwd_d128_kernel<0, 2> : attn_fwd_d128_kernel<0, 0>);
+  else if (pp == 2) kern = (var & 1) ? attn_fwd_d128_kernel<2, 1> : attn_fwd_d128_kernel<2, 0>;
+  int smem_bytes = A_SMEM_BYTES;
+  if (k64) {
+    kern = attn_fwd_d128_k64_kernel;
+    smem_bytes = B_SMEM_BYTES;
   }
   if (kern == nullptr) return M4D_ERR_UNSUPPORTED;
-  rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM_BYTES),
+  rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                "cudaFuncSetAttribute(attention)");
   if (rc != M4D_OK) return rc;
   AttnParams p;
@@ -512,7 +792,7 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
   p.accumulate = accumulate;
   p.flags = g_debug_flags;
   dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
-  kern<<<grid, A_THREADS, A_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, A_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
   M4D_CHECK_LAUNCH("attn_fwd_d128_kernel");
   return M4D_OK;
 }

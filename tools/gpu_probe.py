@@ -114,8 +114,8 @@ def attn_sweep():
     Q, K, V = (torch.randn(B, L, N, 128, device="cuda", dtype=BF16) for _ in range(3))
     out = torch.empty_like(Q)
     fl = 4.0 * B * N * L * L * 128
-    for pp, var in [(0, v) for v in range(8)] + [(2, 0), (2, 1)] + [(0, v) for v in range(8)]:
-        _lib.lib().m4d_set_debug_flags(0x100 | (pp << 4) | var)
+    for pp, var in [(0, 0), (0, 2), (0, 0), (0, 2), (0, 0), (0, 2)]:
+        _lib.lib().m4d_set_debug_flags(0x600 if pp == 64 else (0x200 | 0x100 | (pp << 4) | var))
         o = ops.attention(q.cuda(), k.cuda(), v.cuda())
         e = rel(o.float().cpu(), ref)
         ops.attention(Q, K, V, out=out)
