@@ -96,18 +96,22 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
       const float* grow =
           ep.gate ? ep.gate + (m / ep.rows_per_batch) * ep.gate_bstride + n0 : nullptr;
       if (full) {
+        // all residual loads first: `out` may alias `residual` (x is updated in place), so the
+        // compiler must not be left to interleave dependent load/store round trips
+        float4 rr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rr[q] = *reinterpret_cast<const float4*>(rrow + q * 4);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float4 rr = *reinterpret_cast<const float4*>(rrow + q * 4);
           float4 g = grow ? __ldg(reinterpret_cast<const float4*>(grow + q * 4))
                           : make_float4(1.f, 1.f, 1.f, 1.f);
-          float4 o;
-          o.x = rr.x + v[q * 4 + 0] * g.x;
-          o.y = rr.y + v[q * 4 + 1] * g.y;
-          o.z = rr.z + v[q * 4 + 2] * g.z;
-          o.w = rr.w + v[q * 4 + 3] * g.w;
-          *reinterpret_cast<float4*>(orow + q * 4) = o;
+          rr[q].x += v[q * 4 + 0] * g.x;
+          rr[q].y += v[q * 4 + 1] * g.y;
+          rr[q].z += v[q * 4 + 2] * g.z;
+          rr[q].w += v[q * 4 + 3] * g.w;
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(orow + q * 4) = rr[q];
       } else {
         for (int i = 0; i < 32; ++i)
           if (n0 + i < N) orow[i] = rrow[i] + v[i] * (grow ? grow[i] : 1.f);
@@ -148,10 +152,28 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
   }
 }
 
+// Tile rasterisation: N is cut into panels of `pw` tile-columns whose weight slab
+// (pw * 256 * K * 2 B) fits the L2 next to the streaming A operand; inside a panel tiles run
+// n-fastest so the CTAs in flight share both their A rows and the panel's weights.  Without
+// panels a K = 13824 / N = 13824 weight matrix (141 MB > 126 MB L2) is re-streamed from HBM by
+// every wave of CTAs.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int pw, int& m_blk,
+                                            int& n_blk) {
+  const int per_panel = num_m * pw;
+  int panel = tile / per_panel;
+  const int full_panels = num_n / pw;            // the last panel may be narrower
+  if (panel > full_panels) panel = full_panels;
+  const int n0 = panel * pw;
+  const int w = min(pw, num_n - n0);
+  const int local = tile - panel * per_panel;
+  m_blk = local / w;
+  n_blk = n0 + local - m_blk * w;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    int M, int N, int K, GemmEpi ep) {
+                    int M, int N, int K, int pw, GemmEpi ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -195,7 +217,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        int m_blk, n_blk;
+        tile_coords(tile, num_m, num_n, pw, m_blk, n_blk);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_s = smem + stage * G_STAGE_BYTES;
@@ -248,12 +271,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      int m_blk, n_blk;
+      tile_coords(tile, num_m, num_n, pw, m_blk, n_blk);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const long long m = static_cast<long long>(m_blk) * GM + quad * 32 + lane;
       const bool row_ok = m < M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * GN;
+      if (EPI == M4D_EPI_GATE_RESIDUAL_F32) {
+        // warm the L2->L1 path of this row's residual (256 fp32 = 8 lines) before the first
+        // dependent load: under HBM load the per-chunk load latency is otherwise serialised
+        // 8 times per tile and the epilogue, not the MMA main loop, paces the kernel.
+        if (row_ok) {
+          const float* rrow = ep.res + m * ep.ldr + static_cast<long long>(n_blk) * GN;
+#pragma unroll
+          for (int c = 0; c < GN / 32; ++c)
+            if (n_blk * GN + c * 32 < N)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(rrow + c * 32));
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < GN / 32; ++c) {
         const int n0 = n_blk * GN + c * 32;
@@ -288,7 +324,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   }
   const int tiles = ((M + GM - 1) / GM) * ((N + GN - 1) / GN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, G_THREADS, G_SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  // panel width: weight slab of a panel <= ~48 MB, panels of (nearly) equal width
+  const int num_n = (N + GN - 1) / GN;
+  const long long slab = static_cast<long long>(GN) * K * 2;
+  int pw_max = static_cast<int>((48ll << 20) / (slab > 0 ? slab : 1));
+  if (pw_max < 1) pw_max = 1;
+  const int panels = (num_n + pw_max - 1) / pw_max;
+  const int pw = (num_n + panels - 1) / panels;
+  kern<<<grid, G_THREADS, G_SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, pw, ep);
   M4D_CHECK_LAUNCH("gemm_bf16_tn_kernel");
   return M4D_OK;
 }

@@ -105,6 +105,44 @@ def attn():
                       f" rel vs ours {rel(out.float(), o2.transpose(1, 2).float()):.3e}", flush=True)
 
 
+def gemm_shapes():
+    """The four GEMM shapes of a 14B block at 720p (M = 2*50400), CUDA-event timed."""
+    M, C, Fd = 100800, 5120, 13824
+    x = torch.randn(M, C, device="cuda", dtype=BF16)
+    hbuf = torch.randn(M, Fd, device="cuda", dtype=BF16)
+    res = torch.randn(M, C, device="cuda", dtype=torch.float32)
+    gate = torch.randn(2, 6, C, device="cuda", dtype=torch.float32)
+    wq = torch.randn(C, C, device="cuda", dtype=BF16) * 0.02
+    w0 = torch.randn(Fd, C, device="cuda", dtype=BF16) * 0.02
+    w2 = torch.randn(C, Fd, device="cuda", dtype=BF16) * 0.02
+    b5, bF = torch.randn(C, device="cuda", dtype=BF16), torch.randn(Fd, device="cuda", dtype=BF16)
+    outb = torch.empty(M, C, device="cuda", dtype=BF16)
+    cases = [
+        ("qkv   bias->bf16       K5120  N5120 ", lambda: ops.linear(x, wq, b5, out=outb), 2.0 * M * C * C),
+        ("o     gate-residual    K5120  N5120 ", lambda: ops.linear(x, wq, b5, ops.EPI_GATE_RESIDUAL_F32, out=res, residual=res,
+                                                                   gate=gate[:, 2], gate_batch_stride=6 * C, rows_per_batch=M // 2), 2.0 * M * C * C),
+        ("ffn0  bias+gelu        K5120  N13824", lambda: ops.linear(x, w0, bF, ops.EPI_GELU_TANH, out=hbuf), 2.0 * M * C * Fd),
+        ("ffn2  gate-residual    K13824 N5120 ", lambda: ops.linear(hbuf, w2, b5, ops.EPI_GATE_RESIDUAL_F32, out=res, residual=res,
+                                                                   gate=gate[:, 5], gate_batch_stride=6 * C, rows_per_batch=M // 2), 2.0 * M * C * Fd),
+    ]
+    for name, fn, fl in cases:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+            s_.record(); fn(); e_.record(); torch.cuda.synchronize()
+            ts.append(s_.elapsed_time(e_))
+        ms = min(ts)
+        print(f"{name}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+    # correctness spot check of the rasterisation on a many-panel shape
+    a = rnd((1000, 512), 1); w = rnd((13824, 512), 2, 0.05)
+    o = ops.linear(a.cuda(), w.cuda(), None).float()
+    ref = a.cuda().float() @ w.cuda().float().t()
+    print("raster check rel:", rel(o, ref))
+
+
 def attn_sweep():
     """Polynomial-exp2 share sweep (debug flags 0x10 | PP) at the bench shape + parity."""
     ar = O.Arith(True)
@@ -134,4 +172,4 @@ def attn_sweep():
 
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep}[sys.argv[1]]()
+    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep, "gemm_shapes": gemm_shapes}[sys.argv[1]]()
