@@ -10,11 +10,14 @@
 //   warp 0   TMA producer   : 128x64 A tile + 256x64 W tile per stage, 4-stage mbarrier ring
 //   warp 1   MMA issuer     : one elected thread issues tcgen05.mma (M128 N256 K16) into TMEM
 //   warp 2   TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double-buffered)
-//   warps 4-7 epilogue      : tcgen05.ld -> fused epilogue -> global
+//   warps 4-11 epilogue     : two warpgroups, each drains one 128-column half of the
+//                             accumulator: tcgen05.ld -> fused epilogue -> global
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Epilogues reproduce the reference's autocast rounding: the Linear result is rounded to bf16
 // before anything else touches it (oracle/dit_oracle.py Arith.linear).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -25,7 +28,7 @@ constexpr int G_A_BYTES = GM * GK * 2;            // 16 KB
 constexpr int G_B_BYTES = GN * GK * 2;            // 32 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_SMEM_BYTES = GSTAGES * G_STAGE_BYTES + 256 + 1024;  // + barriers + align slack
-constexpr int G_THREADS = 256;
+constexpr int G_THREADS = 384;               // 4 control warps + 2 epilogue warpgroups
 
 struct GemmEpi {
   const bf16* bias;      // [N] or null
@@ -197,7 +200,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     fence_mbar_init();
   }
@@ -268,6 +271,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;              // which 128-column half this warpgroup drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -285,13 +289,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (row_ok) {
           const float* rrow = ep.res + m * ep.ldr + static_cast<long long>(n_blk) * GN;
 #pragma unroll
-          for (int c = 0; c < GN / 32; ++c)
+          for (int c = half * 4; c < half * 4 + 4; ++c)
             if (n_blk * GN + c * 32 < N)
               asm volatile("prefetch.global.L1 [%0];" ::"l"(rrow + c * 32));
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < GN / 32; ++c) {
+      for (int c = half * 4; c < half * 4 + 4; ++c) {
         const int n0 = n_blk * GN + c * 32;
         if (n0 >= N) break;  // warp-uniform
         uint32_t r[32];
@@ -327,7 +331,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   // panel width: weight slab of a panel <= ~48 MB, panels of (nearly) equal width
   const int num_n = (N + GN - 1) / GN;
   const long long slab = static_cast<long long>(GN) * K * 2;
-  int pw_max = static_cast<int>((48ll << 20) / (slab > 0 ? slab : 1));
+  static long long budget = 0;
+  if (budget == 0) {
+    const char* e = getenv("M4D_GEMM_PANEL_MB");   // development knob
+    budget = (e ? atoll(e) : 48) << 20;
+  }
+  int pw_max = static_cast<int>(budget / (slab > 0 ? slab : 1));
   if (pw_max < 1) pw_max = 1;
   const int panels = (num_n + pw_max - 1) / pw_max;
   const int pw = (num_n + panels - 1) / panels;

@@ -122,6 +122,7 @@ def gemm_shapes():
         ("o     gate-residual    K5120  N5120 ", lambda: ops.linear(x, wq, b5, ops.EPI_GATE_RESIDUAL_F32, out=res, residual=res,
                                                                    gate=gate[:, 2], gate_batch_stride=6 * C, rows_per_batch=M // 2), 2.0 * M * C * C),
         ("ffn0  bias+gelu        K5120  N13824", lambda: ops.linear(x, w0, bF, ops.EPI_GELU_TANH, out=hbuf), 2.0 * M * C * Fd),
+        ("ffn0' bias->bf16       K5120  N13824", lambda: ops.linear(x, w0, bF, out=hbuf), 2.0 * M * C * Fd),
         ("ffn2  gate-residual    K13824 N5120 ", lambda: ops.linear(hbuf, w2, b5, ops.EPI_GATE_RESIDUAL_F32, out=res, residual=res,
                                                                    gate=gate[:, 5], gate_batch_stride=6 * C, rows_per_batch=M // 2), 2.0 * M * C * Fd),
     ]
