@@ -26,44 +26,68 @@ __device__ __forceinline__ float wsum(float v) {
 }
 __device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(x / (1.f + __expf(-x))); }
 
-// RMS_norm (wan_vae.py:43-58: F.normalize over channels * sqrt(C) * gamma) [+ SiLU], one warp
-// per pixel, C <= 512, C % 4 == 0.  May run in place.
+// RMS_norm (wan_vae.py:43-58: F.normalize over channels * sqrt(C) * gamma) [+ SiLU].
+// Every thread owns one 16-byte vector (8 channels) of a pixel, so a pixel is shared by
+// LPP = C/8 consecutive threads (12 / 24 / 48 for C = 96 / 192 / 384 — not warp-aligned, hence
+// the per-pixel sum of squares is combined through shared memory rather than shuffles).  A
+// block covers 256 / LPP pixels per iteration and keeps RN_ITERS independent iterations in
+// flight per thread: the first version (one warp per pixel, one load in flight) ran at ~1/5 of
+// the HBM roofline (profiles/launches_vae_r01.md).  In place allowed.
+constexpr int RN_ITERS = 4;
 __global__ void __launch_bounds__(256)
 rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, bf16* __restrict__ out,
                        long long pixels, int C, int do_silu) {
-  const long long pix = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (pix >= pixels) return;
-  const bf16* xr = x + pix * C;
-  const int nvec = C >> 2;
-  float4 v[4];
-  float ss = 0.f;
+  __shared__ float part[RN_ITERS][256];
+  const int lpp = C >> 3;                         // lanes (16-byte vectors) per pixel
+  const int ppb = 256 / lpp;                      // pixels per block-iteration
+  const int lp = threadIdx.x / lpp;               // local pixel
+  const int lv = threadIdx.x - lp * lpp;          // vector within the pixel
+  const bool active = lp < ppb;
+  const long long pix0 = (static_cast<long long>(blockIdx.x) * RN_ITERS) * ppb + lp;
+  uint4 v[RN_ITERS];
+  float ss[RN_ITERS];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      v[i] = ld4(xr + vi * 4);
-      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-    }
-  }
-  const float nrm = fmaxf(bf16_round(sqrtf(wsum(ss))), 1e-12f);
-  const float sc = sqrtf(static_cast<float>(C));
-  bf16* orow = out + pix * C;
+  for (int it = 0; it < RN_ITERS; ++it) {
+    const long long pix = pix0 + static_cast<long long>(it) * ppb;
+    ss[it] = 0.f;
+    if (active && pix < pixels) {
+      v[it] = *reinterpret_cast<const uint4*>(x + pix * C + lv * 8);
+      const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const float4 g = ld4(gamma + vi * 4);
-      float4 y;
-      y.x = bf16_round(bf16_round(bf16_round(v[i].x / nrm) * sc) * g.x);
-      y.y = bf16_round(bf16_round(bf16_round(v[i].y / nrm) * sc) * g.y);
-      y.z = bf16_round(bf16_round(bf16_round(v[i].z / nrm) * sc) * g.z);
-      y.w = bf16_round(bf16_round(bf16_round(v[i].w / nrm) * sc) * g.w);
-      if (do_silu) {
-        y.x = silu_bf16r(y.x); y.y = silu_bf16r(y.y); y.z = silu_bf16r(y.z); y.w = silu_bf16r(y.w);
+      for (int e = 0; e < 4; ++e) {
+        const float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
+        ss[it] += a * a + b * b;
       }
-      st4(orow + vi * 4, y);
     }
+    part[it][threadIdx.x] = ss[it];
+  }
+  __syncthreads();
+  const uint4 g4 = active ? *reinterpret_cast<const uint4*>(gamma + lv * 8) : make_uint4(0, 0, 0, 0);
+  const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+  const float sc = sqrtf(static_cast<float>(C));
+#pragma unroll
+  for (int it = 0; it < RN_ITERS; ++it) {
+    const long long pix = pix0 + static_cast<long long>(it) * ppb;
+    if (!(active && pix < pixels)) continue;
+    float tot = 0.f;
+    const float* pp = &part[it][lp * lpp];
+    for (int i = 0; i < lpp; ++i) tot += pp[i];
+    const float nrm = fmaxf(bf16_round(sqrtf(tot)), 1e-12f);
+    const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
+      const float ga = __uint_as_float(gw[e] << 16), gb = __uint_as_float(gw[e] & 0xFFFF0000u);
+      a = bf16_round(bf16_round(bf16_round(a / nrm) * sc) * ga);
+      b = bf16_round(bf16_round(bf16_round(b / nrm) * sc) * gb);
+      if (do_silu) {
+        a = silu_bf16r(a);
+        b = silu_bf16r(b);
+      }
+      o[e] = pack_bf16(a, b);
+    }
+    *reinterpret_cast<uint4*>(out + pix * C + lv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -154,28 +178,47 @@ __global__ void __launch_bounds__(256)
 groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                        const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ out,
                        int F, int HW, int C, int cpg, float eps) {
-  const long long nvec_total = static_cast<long long>(F) * HW * (C >> 2);
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= nvec_total) return;
-  const int nvec = C >> 2;
-  const int v = static_cast<int>(idx % nvec);
-  const int f = static_cast<int>(idx / (static_cast<long long>(HW) * nvec));
-  const int g = (v * 4) / cpg;
-  const float n = static_cast<float>(HW) * cpg;
-  const float mean = stats[f * 64 + g * 2] / n;
-  const float var = fmaxf(stats[f * 64 + g * 2 + 1] / n - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  const float4 a = ld4(x + idx * 4), ww = ld4(w + v * 4), bb = ld4(b + v * 4);
-  float4 y;
-  y.x = bf16_round((a.x - mean) * rstd * ww.x + bb.x);
-  y.y = bf16_round((a.y - mean) * rstd * ww.y + bb.y);
-  y.z = bf16_round((a.z - mean) * rstd * ww.z + bb.z);
-  y.w = bf16_round((a.w - mean) * rstd * ww.w + bb.w);
-  y.x *= bf16_round(1.f / (1.f + __expf(-y.x)));
-  y.y *= bf16_round(1.f / (1.f + __expf(-y.y)));
-  y.z *= bf16_round(1.f / (1.f + __expf(-y.z)));
-  y.w *= bf16_round(1.f / (1.f + __expf(-y.w)));
-  st4(out + idx * 4, y);
+  // one thread = two 16-byte vectors (8 channels each) of the same channel slot, 128 pixels apart
+  const int nvec = C >> 3;
+  const long long per_frame = static_cast<long long>(HW) * nvec;
+  const long long total = static_cast<long long>(F) * per_frame;
+  const long long i0 = (static_cast<long long>(blockIdx.x) * 2) * 256 + threadIdx.x;
+  uint4 v[2];
+  bool ok[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const long long idx = i0 + k * 256;
+    ok[k] = idx < total;
+    if (ok[k]) v[k] = *reinterpret_cast<const uint4*>(x + idx * 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const long long idx = i0 + k * 256;
+    if (!ok[k]) continue;
+    const int vi = static_cast<int>(idx % nvec);
+    const int f = static_cast<int>(idx / per_frame);
+    const float n = static_cast<float>(HW) * cpg;
+    const uint4 w4 = *reinterpret_cast<const uint4*>(w + vi * 8);
+    const uint4 b4 = *reinterpret_cast<const uint4*>(b + vi * 8);
+    const uint32_t xs[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+    const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (vi * 8 + e * 2) / cpg;           // both halves of a pair share a group (cpg % 2 == 0)
+      const float mean = stats[f * 64 + g * 2] / n;
+      const float var = fmaxf(stats[f * 64 + g * 2 + 1] / n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float a0 = __uint_as_float(xs[e] << 16), a1 = __uint_as_float(xs[e] & 0xFFFF0000u);
+      a0 = bf16_round((a0 - mean) * rstd * __uint_as_float(ws[e] << 16) + __uint_as_float(bs[e] << 16));
+      a1 = bf16_round((a1 - mean) * rstd * __uint_as_float(ws[e] & 0xFFFF0000u) +
+                      __uint_as_float(bs[e] & 0xFFFF0000u));
+      a0 *= bf16_round(1.f / (1.f + __expf(-a0)));
+      a1 *= bf16_round(1.f / (1.f + __expf(-a1)));
+      o[e] = pack_bf16(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // row softmax of fp32 logits * scale -> bf16 probabilities (the VAE AttentionBlock's single
@@ -233,10 +276,10 @@ extern "C" int m4d_rmsnorm_silu_cl(const void* x, const void* gamma, void* out, 
                                    int C, int do_silu, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(x && gamma && out && pixels > 0, M4D_ERR_BAD_SHAPE);
-  M4D_REQUIRE(C % 4 == 0 && C <= 512 && C > 0, M4D_ERR_UNSUPPORTED);
-  M4D_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
-              M4D_ERR_ALIGN);
-  const long long blocks = (pixels + 7) / 8;
+  M4D_REQUIRE(C % 8 == 0 && C <= 2048 && C > 0, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma), M4D_ERR_ALIGN);
+  const int ppb = 256 / (C / 8);
+  const long long blocks = (pixels + static_cast<long long>(ppb) * RN_ITERS - 1) / (static_cast<long long>(ppb) * RN_ITERS);
   M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
   rmsnorm_silu_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
       static_cast<const bf16*>(x), static_cast<const bf16*>(gamma), static_cast<bf16*>(out), pixels, C,
@@ -290,6 +333,7 @@ extern "C" int m4d_groupnorm_swish_cl(const void* x, const void* weight, const v
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(x && weight && bias && out && stats_ws && F > 0 && HW > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(groups == 32 && C % (groups * 4) == 0 && C <= 1024, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(aligned16(x) && aligned16(out) && aligned16(weight) && aligned16(bias), M4D_ERR_ALIGN);
   M4D_REQUIRE(F <= 65535, M4D_ERR_BAD_SHAPE);
   int rc = cuda_ok(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 64 * F, stream), "memset(groupnorm stats)");
   if (rc != M4D_OK) return rc;
@@ -300,8 +344,8 @@ extern "C" int m4d_groupnorm_swish_cl(const void* x, const void* weight, const v
   if (chunks < 1) chunks = 1;
   groupnorm_stats_kernel<<<dim3(chunks, F), 256, 0, stream>>>(static_cast<const bf16*>(x), stats_ws, HW, C, cpg);
   M4D_CHECK_LAUNCH("groupnorm_stats_kernel");
-  const long long nvec = static_cast<long long>(F) * HW * (C / 4);
-  const long long blocks = (nvec + 255) / 256;
+  const long long nvec = static_cast<long long>(F) * HW * (C / 8);
+  const long long blocks = (nvec + 511) / 512;
   M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
   groupnorm_swish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
       static_cast<const bf16*>(x), stats_ws, static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),

@@ -64,6 +64,9 @@ def main():
             "latent_shape": list(lat.shape), "finite": finite, "kernel_launches_per_roundtrip": launches,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "stages": {}}
     total = 0.0
+    if not res:
+        print(json.dumps(line))
+        return
     for k, ts in res.items():
         ms = min(ts)
         total += ms
