@@ -24,7 +24,9 @@ __device__ __forceinline__ float wsum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(x / (1.f + __expf(-x))); }
+// fast division: these passes were instruction-bound on IEEE divides, not HBM-bound; the
+// results are re-rounded to bf16 (2^-9) so the <= 2 ulp fp32 error of __fdividef is invisible
+__device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(__fdividef(x, 1.f + __expf(-x))); }
 
 // RMS_norm (wan_vae.py:43-58: F.normalize over channels * sqrt(C) * gamma) [+ SiLU].
 // Every thread owns one 16-byte vector (8 channels) of a pixel, so a pixel is shared by
@@ -73,14 +75,15 @@ rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamm
     const float* pp = &part[it][lp * lpp];
     for (int i = 0; i < lpp; ++i) tot += pp[i];
     const float nrm = fmaxf(bf16_round(sqrtf(tot)), 1e-12f);
+    const float inv = 1.0f / nrm;
     const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
       const float ga = __uint_as_float(gw[e] << 16), gb = __uint_as_float(gw[e] & 0xFFFF0000u);
-      a = bf16_round(bf16_round(bf16_round(a / nrm) * sc) * ga);
-      b = bf16_round(bf16_round(bf16_round(b / nrm) * sc) * gb);
+      a = bf16_round(bf16_round(bf16_round(a * inv) * sc) * ga);
+      b = bf16_round(bf16_round(bf16_round(b * inv) * sc) * gb);
       if (do_silu) {
         a = silu_bf16r(a);
         b = silu_bf16r(b);
@@ -113,16 +116,24 @@ __global__ void upsample2x_cl_kernel(const bf16* __restrict__ x, bf16* __restric
 __global__ void planar_to_cl_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long P,
                                     int C, int Cpad, const float* __restrict__ div,
                                     const float* __restrict__ add) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= P * Cpad) return;
-  const int c = static_cast<int>(idx % Cpad);
-  const long long pix = idx / Cpad;
-  float v = 0.f;
-  if (c < C) {
-    v = __bfloat162float(x[c * P + pix]);
-    if (div != nullptr) v = bf16_round(bf16_round(v / div[c]) + add[c]);
+  // one thread = one pixel: C coalesced plane reads, Cpad*2 bytes written as 16-byte vectors
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= P) return;
+  uint4* o = reinterpret_cast<uint4*>(out + pix * Cpad);
+  for (int c0 = 0; c0 < Cpad; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      v[e] = 0.f;
+      if (c < C) {
+        v[e] = __bfloat162float(x[c * P + pix]);
+        if (div != nullptr) v[e] = bf16_round(bf16_round(v[e] / div[c]) + add[c]);
+      }
+    }
+    o[c0 >> 3] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                            pack_bf16(v[6], v[7]));
   }
-  out[idx] = __float2bfloat16_rn(v);
 }
 
 // channels-last [P, C] -> planar [C, P] with the encoder's (mu - mean) * inv_std
@@ -213,8 +224,8 @@ groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ sta
       a0 = bf16_round((a0 - mean) * rstd * __uint_as_float(ws[e] << 16) + __uint_as_float(bs[e] << 16));
       a1 = bf16_round((a1 - mean) * rstd * __uint_as_float(ws[e] & 0xFFFF0000u) +
                       __uint_as_float(bs[e] & 0xFFFF0000u));
-      a0 *= bf16_round(1.f / (1.f + __expf(-a0)));
-      a1 *= bf16_round(1.f / (1.f + __expf(-a1)));
+      a0 *= bf16_round(__fdividef(1.f, 1.f + __expf(-a0)));
+      a1 *= bf16_round(__fdividef(1.f, 1.f + __expf(-a1)));
       o[e] = pack_bf16(a0, a1);
     }
     *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -306,7 +317,8 @@ extern "C" int m4d_planar_to_cl(const void* x, void* out, long long P, int C, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(x && out && P > 0 && C > 0 && Cpad >= C, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE((div == nullptr) == (add == nullptr), M4D_ERR_BAD_SHAPE);
-  const long long blocks = (P * Cpad + 255) / 256;
+  M4D_REQUIRE(Cpad % 8 == 0 && aligned16(out), M4D_ERR_ALIGN);
+  const long long blocks = (P + 255) / 256;
   M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
   planar_to_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(out), P, C, Cpad, div, add);

@@ -148,6 +148,14 @@ class AutoencoderKLWan(nn.Module):
             self._consts = (mean, inv_std)
         return self._consts
 
+    def _input_cl(self, x: Tensor, in_scale: float, in_shift: float) -> Tensor:
+        if in_scale == 1.0 and in_shift == 0.0:
+            return ops.planar_to_cl(x, 32)
+        dev = x.device
+        div = torch.full((3,), 1.0 / in_scale, device=dev, dtype=torch.float32)
+        add = torch.full((3,), in_shift, device=dev, dtype=torch.float32)
+        return ops.planar_to_cl(x, 32, div, add)
+
     def _conv(self, x: Tensor, name: str, kernel, cout: int, pad, **kw) -> Tensor:
         w = self._p(name + ".weight")
         return ops.conv_cl(x, self._packed.get(name, w), self._p(name + ".bias"), cout, kernel, pad=pad, **kw)
@@ -219,8 +227,11 @@ class AutoencoderKLWan(nn.Module):
         """x [3, F, H, W] (F = 1 + 4k) -> params [2z, 1 + k, H/8, W/8]  (vae:520-547)."""
         cfg = self.cfg
         layers = encoder_layers(cfg)
-        h = ops.conv_in3(x, self._p("encoder.conv1.weight"), self._p("encoder.conv1.bias"), 3,
-                         in_scale, in_shift)
+        # 3-channel input: zero-padded to 32 channels so the first conv also runs on the tensor
+        # cores (K = 27 x 32); the optional `x*2-1` is fused into the layout pass
+        xc = self._input_cl(x, in_scale, in_shift)
+        h = self._conv(xc, "encoder.conv1", (3, 3, 3), layers[0][3], (2, 1, 1))
+        del xc
         h = self._run(h, layers[1:-1])
         _, hname, cin, cout = layers[-1]
         ops.rmsnorm_silu_cl(h, self._p(hname + ".0.gamma"), inplace=True)
@@ -314,7 +325,7 @@ class VAEEncoderadaptor(_Adaptor):
     kind = "encoder"
 
     def _forward_one(self, x: Tensor) -> Tensor:          # x [3, F, H, W]
-        h = ops.conv_in3(x, self._p("conv_in.weight"), self._p("conv_in.bias"), 1)
+        h = self._conv(ops.planar_to_cl(x, 32), "conv_in", self.ch)
         h = self._resnet(h, "down.0.block.0")
         ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True)
         out = torch.empty_like(x)
@@ -327,7 +338,7 @@ class VAEDecoderadaptor(_Adaptor):
     kind = "decoder"
 
     def _forward_one(self, z: Tensor) -> Tensor:
-        h = ops.conv_in3(z, self._p("conv_in.weight"), self._p("conv_in.bias"), 1)
+        h = self._conv(ops.planar_to_cl(z, 32), "conv_in", self.ch)
         h = self._resnet(h, "up.0.block.0")
         h = self._resnet(h, "up.0.block.1")
         ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True)
