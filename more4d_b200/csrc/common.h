@@ -90,4 +90,10 @@ inline int sm_count() {
 
 extern int g_debug_flags;  // see m4d_set_debug_flags
 
+// 2-CTA (cta_group::2) GEMM, gemm2.cu
+int gemm2_dispatch(const void* a, long long lda, const void* w, long long ldw, const void* bias, void* out,
+                   long long ldo, int M, int N, int K, int epilogue, const float* residual, long long ldr,
+                   const float* gate, long long gate_batch_stride, int rows_per_batch,
+                   cudaStream_t stream);
+
 }  // namespace m4d

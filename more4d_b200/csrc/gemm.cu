@@ -28,6 +28,7 @@ constexpr int G_A_BYTES = GM * GK * 2;            // 16 KB
 constexpr int G_B_BYTES = GN * GK * 2;            // 32 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_SMEM_BYTES = GSTAGES * G_STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int G_DEFAULT_2CTA = 1;           // 1: route large GEMMs to the cta_group::2 kernel (gemm2.cu)
 constexpr int G_THREADS = 384;               // 4 control warps + 2 epilogue warpgroups
 
 struct GemmEpi {
@@ -372,6 +373,16 @@ extern "C" int m4d_gemm_bf16(const void* a, long long lda, const void* w, long l
   if (epilogue == M4D_EPI_ADD_BF16) M4D_REQUIRE(residual != nullptr && ldr >= N, M4D_ERR_BAD_SHAPE);
   if (bias) M4D_REQUIRE(aligned16(bias), M4D_ERR_ALIGN);
 
+  // 2-CTA kernel (gemm2.cu) for the large-M block GEMMs; debug flag 0x1000 forces it on,
+  // 0x2000 forces it off, otherwise G_DEFAULT_2CTA decides.
+  {
+    const bool want = (g_debug_flags & 0x2000) ? false : ((g_debug_flags & 0x1000) ? true : (G_DEFAULT_2CTA != 0));
+    const bool has = epilogue == M4D_EPI_BF16 || epilogue == M4D_EPI_GELU_TANH ||
+                     epilogue == M4D_EPI_GATE_RESIDUAL_F32;
+    if (want && has && M >= 1024 && N >= 256)
+      return gemm2_dispatch(a, lda, w, ldw, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate,
+                            gate_batch_stride, rows_per_batch, stream);
+  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};

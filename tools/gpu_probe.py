@@ -144,6 +144,44 @@ def gemm_shapes():
     print("raster check rel:", rel(o, ref))
 
 
+def gemm2():
+    """2-CTA GEMM (debug flag 0x1000): correctness on small / ragged shapes, then timing."""
+    _lib.lib().m4d_set_debug_flags(0x1000)
+    for (M, N, K) in [(1024, 256, 64), (1024, 256, 512), (1300, 512, 192), (4096, 5120, 5120)]:
+        a, w, b = rnd((M, K), 1), rnd((N, K), 2, 0.05), rnd((N,), 3, 0.1)
+        out = ops.linear(a.cuda(), w.cuda(), b.cuda())
+        torch.cuda.synchronize()
+        ref = (a.cuda().float() @ w.cuda().float().t() + b.cuda().float())
+        print(f"gemm2 {M}x{N}x{K}: rel={rel(out.float(), ref):.3e}", flush=True)
+    for flags, name in ((0x2000, "1-CTA"), (0x1000, "2-CTA"), (0x2000, "1-CTA"), (0x1000, "2-CTA")):
+        _lib.lib().m4d_set_debug_flags(flags)
+        print("==", name, flush=True)
+        gemm_shapes()
+    _lib.lib().m4d_set_debug_flags(0)
+
+
+def gemm2_k():
+    """Per-k-block vs per-tile cost of the 1-CTA and 2-CTA GEMM kernels."""
+    M, N = 16384, 5120
+    for K in (512, 2048, 8192):
+        a = torch.randn(M, K, device="cuda", dtype=BF16)
+        w = torch.randn(N, K, device="cuda", dtype=BF16) * 0.02
+        out = torch.empty(M, N, device="cuda", dtype=BF16)
+        for flags, name in ((0x2000, "1-CTA"), (0x1000, "2-CTA")):
+            _lib.lib().m4d_set_debug_flags(flags)
+            for _ in range(2):
+                ops.linear(a, w, None, out=out)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+                s_.record(); ops.linear(a, w, None, out=out); e_.record(); torch.cuda.synchronize()
+                ts.append(s_.elapsed_time(e_))
+            ms = min(ts)
+            print(f"K={K} {name}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    _lib.lib().m4d_set_debug_flags(0)
+
+
 def attn_sweep():
     """Polynomial-exp2 share sweep (debug flags 0x10 | PP) at the bench shape + parity."""
     ar = O.Arith(True)
@@ -173,4 +211,4 @@ def attn_sweep():
 
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep, "gemm_shapes": gemm_shapes}[sys.argv[1]]()
+    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep, "gemm_shapes": gemm_shapes, "gemm2": gemm2, "gemm2_k": gemm2_k}[sys.argv[1]]()
