@@ -1,0 +1,71 @@
+"""C-ABI checks that need no GPU: libmore4d_sm100.so loads, exports every function that
+include/more4d_b200.h declares, the ctypes table binds exactly that set, and — on a box without
+an sm_100 device — the library reports M4D_ERR_NO_DEVICE / M4D_ERR_CUDA instead of computing
+anywhere else.  No compute entry point is called with real data here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from more4d_b200 import _lib, build as _build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        _build.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_header_symbol(lib):
+    names = _lib.header_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/more4d_b200.h but not exported: {missing}"
+
+
+def test_ctypes_table_matches_header(lib):
+    assert sorted(_lib._SIGNATURES) == _lib.header_symbols()
+    # argument counts in the ctypes table agree with the prototypes in the header
+    with open(_lib.HEADER_PATH) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    for name, (_, args) in _lib._SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^)]*)\)", text)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), f"{name}: header has {n} parameters, ctypes table {len(args)}"
+
+
+def test_version_and_error_strings(lib):
+    assert lib.m4d_version() >= 100
+    seen = set()
+    for code in (0, -1, -2, -3, -4, -5, -6):
+        s = lib.m4d_error_string(code)
+        assert isinstance(s, bytes) and s
+        seen.add(s)
+    assert len(seen) == 7
+
+
+def test_epilogue_ids_match_header():
+    with open(_lib.HEADER_PATH) as f:
+        text = f.read()
+    ids = dict((k, int(v)) for k, v in re.findall(r"(M4D_EPI_[A-Z0-9_]+)\s*=\s*(\d+)", text))
+    assert ids["M4D_EPI_BF16"] == _lib.EPI_BF16
+    assert ids["M4D_EPI_GELU_TANH"] == _lib.EPI_GELU_TANH
+    assert ids["M4D_EPI_GELU_ERF"] == _lib.EPI_GELU_ERF
+    assert ids["M4D_EPI_F32"] == _lib.EPI_F32
+    assert ids["M4D_EPI_GATE_RESIDUAL_F32"] == _lib.EPI_GATE_RESIDUAL_F32
+    assert ids["M4D_EPI_ADD_BF16"] == _lib.EPI_ADD_BF16
+    assert ids["M4D_EPI_F32_RAW"] == _lib.EPI_F32_RAW
+
+
+def test_no_device_is_an_error_not_a_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is visible")
+    assert lib.m4d_device_check() != 0
+    _lib._device_ok = None
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        _lib.require_device()
