@@ -208,72 +208,93 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tma_load_4d(sV + sv * A_TILE_BYTES + h * A_HALF_BYTES, &tmV, &v_full[sv], h * 64, head,
                       j * A_BKV, b);
       }
-    } else if (warp == 9 && lane == 0) {
+    } else if (warp == 9) {
+      // The whole warp runs this loop converged and ONE elected lane issues: operands then live
+      // in uniform registers and every descriptor is {lo + compile-time offset, constant hi}.
+      // With `if (lane == 0)` the compiler wraps each tcgen05.mma in an R2UR/ELECT loop and
+      // rebuilds the descriptor (~14 SASS instructions per 64-clock MMA): the issue rate was
+      // co-critical with the tensor pipe.
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);   // V is MN-major (d contiguous)
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
-      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      // V descriptor strides: 64-wide d chunks are 16 KB apart, 8-key groups 1 KB apart.
-      const uint32_t v_lbo = A_HALF_BYTES, v_sbo = 1024;
+      // K-major SW128 tiles (Q, K): LBO 16 B, SBO 1024 B.  V (MN-major): 64-wide d chunks are
+      // 16 KB apart (LBO), 8-key groups 1 KB apart (SBO).
+      constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t k_lo = ((smem_u32(sK) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t v_lo = ((smem_u32(sV) >> 4) & 0x3FFF) | ((A_HALF_BYTES >> 4) << 16);
+      const uint32_t tS0 = tmem_base, tO0 = tmem_base + 256;
+      auto dp = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
 
-      auto issue_qk = [&](int t, int sk) {
+      auto issue_qk = [&](int t, int sk) {               // elected lane only
+        const uint32_t a_lo = q_lo + t * (A_TILE_BYTES >> 4), b_lo = k_lo + sk * (A_TILE_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < A_D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * A_HALF_BYTES + (kk & 3) * 32;
-          const uint64_t ad = umma_smem_desc(q_addr + t * A_TILE_BYTES + off, 16, 1024);
-          const uint64_t bd = umma_smem_desc(k_addr + sk * A_TILE_BYTES + off, 16, 1024);
-          umma_ss(tS[t], ad, bd, idesc_qk, kk != 0);
+          const uint32_t off = (kk >> 2) * (A_HALF_BYTES >> 4) + (kk & 3) * 2;
+          umma_ss(tS0 + t * 128, dp(a_lo + off, HI), dp(b_lo + off, HI), idesc_qk, kk != 0);
         }
       };
       // O_t += P_t[:, slice] V[slice, :] — P arrives in NS key-slices so the first PV MMAs
       // overlap the exponentials of the later slices
       constexpr int NS = (VAR == 1) ? 4 : (VAR == 2 ? 1 : 2);
-      auto issue_pv_tile = [&](int t, int sv, int j) {
+      auto issue_pv_tile = [&](int t, int sv, int j, bool leader) {   // whole warp
+        const uint32_t b_lo = v_lo + sv * (A_TILE_BYTES >> 4);
 #pragma unroll
         for (int sl = 0; sl < NS; ++sl) {
           mbar_wait(&p_ready[4 * t + sl], j & 1);
           tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int k4 = 0; k4 < 8 / NS; ++k4) {
-            const int kk = sl * (8 / NS) + k4;
-            const uint64_t bd = umma_smem_desc(v_addr + sv * A_TILE_BYTES + kk * 2048, v_lbo, v_sbo);
-            umma_ts(tO[t], tS[t] + kk * 8, bd, idesc_pv, !(j == 0 && kk == 0));
+            for (int k4 = 0; k4 < 8 / NS; ++k4) {
+              const int kk = sl * (8 / NS) + k4;
+              umma_ts(tO0 + t * 128, tS0 + t * 128 + kk * 8, dp(b_lo + kk * (2048 >> 4), HI), idesc_pv,
+                      !(j == 0 && kk == 0));
+            }
           }
+          __syncwarp();
         }
       };
 
+      const bool leader = elect_one();
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit(&s_full[0]);
-      issue_qk(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&k_empty[0]);
+      if (leader) {
+        issue_qk(0, 0);
+        umma_commit(&s_full[0]);
+        issue_qk(1, 0);
+        umma_commit(&s_full[1]);
+        umma_commit(&k_empty[0]);
+      }
+      __syncwarp();
       for (int j = 0; j < n_kv; ++j) {
         const int sv = j % A_VS;
         const bool last = (j + 1 == n_kv);
         const int sk = (j + 1) % A_KS;
         mbar_wait(&v_full[sv], (j / A_VS) & 1);
-        issue_pv_tile(0, sv, j);
-        if (last) {
-          umma_commit(&o_final[0]);
-        } else {
-          mbar_wait(&k_full[sk], ((j + 1) / A_KS) & 1);
-          tc_fence_after();
-          issue_qk(0, sk);
-          umma_commit(&s_full[0]);
+        issue_pv_tile(0, sv, j, leader);
+        if (!last) mbar_wait(&k_full[sk], ((j + 1) / A_KS) & 1);
+        tc_fence_after();
+        if (leader) {
+          if (last) {
+            umma_commit(&o_final[0]);
+          } else {
+            issue_qk(0, sk);
+            umma_commit(&s_full[0]);
+          }
         }
-        issue_pv_tile(1, sv, j);
-        umma_commit(&v_empty[sv]);
-        if (last) {
-          umma_commit(&o_final[1]);
-        } else {
-          issue_qk(1, sk);
-          umma_commit(&s_full[1]);
-          umma_commit(&k_empty[sk]);
+        __syncwarp();
+        issue_pv_tile(1, sv, j, leader);
+        if (leader) {
+          umma_commit(&v_empty[sv]);
+          if (last) {
+            umma_commit(&o_final[1]);
+          } else {
+            issue_qk(1, sk);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[sk]);
+          }
         }
+        __syncwarp();
       }
     }
   } else {

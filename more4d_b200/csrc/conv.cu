@@ -20,8 +20,7 @@
 // CTA = 256 threads, persistent: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-7 epilogue (bias, residual add, bf16 rounding like the reference's bf16 path; NHWC
 // store, or planar NCTHW store with clamp / sigmoid for the 3-channel model outputs).
-#include "common.h"
-#include "ptx.cuh"
+#include "conv_common.cuh"
 
 namespace m4d {
 
@@ -30,26 +29,6 @@ constexpr int CV_KB = 32;                      // channels per TMA box (64 bytes
 constexpr int CV_A_SUB = 128 * CV_KB * 2;      // 8 KB
 constexpr int CV_THREADS = 256;
 constexpr int CV_SMEM_BUDGET = 200 * 1024;
-
-struct ConvParams {
-  int T_out, H_out, W_out;
-  int Cin, Cout;            // Cin multiple of 32 (as stored), Cout = real output channels
-  int kt, kh, kw, st, sh, sw, pt, ph, pw;
-  int ksub;                 // 32-channel boxes per pipeline stage
-  int NT;                   // output-channel tile (multiple of 16, <= 256)
-  int n_tiles;              // ceil(Cout / NT)
-  int stages;
-  // output addressing: element (t, h, w, n) goes to frame t*t_mul + t_off + n / n_split,
-  // channel n % n_split of a channels-last tensor with out_C channels per pixel
-  void* out;
-  const bf16* residual;     // same addressing as out (NHWC mode only), or null
-  const bf16* bias;         // [Cout] or null
-  int out_C, t_mul, t_off, n_split;
-  int out_mode;             // 0 NHWC bf16; 1 planar NCTHW bf16 (n < Cout)
-  int act;                  // 0 none, 1 clamp(-1,1), 2 sigmoid(y + skip)
-  const bf16* skip;         // planar NCTHW tensor added before the sigmoid (act == 2)
-  long long planar_cstride; // T*H*W of the planar tensors
-};
 
 __device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr) {
   // K-major SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart
@@ -198,63 +177,7 @@ conv_cl_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tmem_ld32(t_row + c0, rr);
         tmem_ld_wait();
         if (!pix_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = __uint_as_float(rr[i]);
-          if (p.bias != nullptr && n0 + i < p.Cout) v[i] += __bfloat162float(p.bias[n0 + i]);
-          v[i] = bf16_round(v[i]);
-        }
-        if (p.out_mode == 0) {
-          const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
-          const int ch = n0 % p.n_split;
-          const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
-          bf16* o = reinterpret_cast<bf16*>(p.out) + off;
-          const int nvalid = min(32, p.Cout - n0);
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            if (p.residual != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = rp[q];
-                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[q * 8 + 2 * e] += __uint_as_float(ww[e] << 16);
-                  v[q * 8 + 2 * e + 1] += __uint_as_float(ww[e] & 0xFFFF0000u);
-                }
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-              u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-              u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-              reinterpret_cast<uint4*>(o)[q] = u;
-            }
-          } else {
-            for (int i = 0; i < nvalid; ++i) {
-              float y = v[i];
-              if (p.residual != nullptr) y += __bfloat162float(p.residual[off + i]);
-              o[i] = __float2bfloat16_rn(y);
-            }
-          }
-        } else {
-          // planar NCTHW output of a few channels (decoder head / adaptor conv_out)
-          const long long pix = (static_cast<long long>(t) * p.H_out + h) * p.W_out + w;
-          for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
-            float y = v[i];
-            const long long off = (n0 + i) * p.planar_cstride + pix;
-            if (p.act == 1) y = fminf(1.f, fmaxf(-1.f, y));
-            if (p.act == 2) {
-              y = bf16_round(y + __bfloat162float(p.skip[off]));
-              y = 1.f / (1.f + __expf(-y));
-            }
-            reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(y);
-          }
-        }
+        conv_store_chunk(p, rr, t, h, w, n0);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -364,6 +287,13 @@ extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin,
   p.out_mode = out_mode; p.act = act;
   p.skip = static_cast<const bf16*>(skip);
   p.planar_cstride = static_cast<long long>(T_out) * H_out * W_out;
+  p.a_stages = 0; p.acc_bufs = 0; p.acc_stride = 0; p.desc_mode = 0;
+
+  // 3x3 (x kt) stride-1 convolutions — almost all of the VAE's FLOPs — take the halo-staging
+  // kernel (conv_halo.cu); debug flag 0x10000 forces the per-tap kernel below.
+  if (!(g_debug_flags & 0x10000) &&
+      conv_halo_eligible(Cin, kt, kh, kw, st, sh, sw, pt, ph, pw, T_in, H_in, W_in, T_out, H_out, W_out))
+    return conv_halo_launch(x, T_in, H_in, W_in, w_packed, Cout_pad, p, stream);
 
   CUtensorMap tmX, tmW;
   {

@@ -1,0 +1,106 @@
+// Shared by the two implicit-GEMM convolution kernels (conv.cu: one TMA box per tap;
+// conv_halo.cu: halo tile staged once per time tap): launch parameters and the epilogue of one
+// 32-channel chunk of one output pixel.
+#pragma once
+#include "common.h"
+#include "ptx.cuh"
+
+namespace m4d {
+
+struct ConvParams {
+  int T_out, H_out, W_out;
+  int Cin, Cout;            // Cin multiple of 32 (as stored), Cout = real output channels
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int ksub;                 // conv.cu: 32-channel boxes per pipeline stage
+  int NT;                   // output-channel tile (multiple of 16, <= 256)
+  int n_tiles;              // ceil(Cout / NT)
+  int stages;               // conv.cu: pipeline stages; conv_halo.cu: weight-ring stages
+  // output addressing: element (t, h, w, n) goes to frame t*t_mul + t_off + n / n_split,
+  // channel n % n_split of a channels-last tensor with out_C channels per pixel
+  void* out;
+  const bf16* residual;     // same addressing as out (NHWC mode only), or null
+  const bf16* bias;         // [Cout] or null
+  int out_C, t_mul, t_off, n_split;
+  int out_mode;             // 0 NHWC bf16; 1 planar NCTHW bf16 (n < Cout)
+  int act;                  // 0 none, 1 clamp(-1,1), 2 sigmoid(y + skip)
+  const bf16* skip;         // planar NCTHW tensor added before the sigmoid (act == 2)
+  long long planar_cstride; // T*H*W of the planar tensors
+  // conv_halo.cu only
+  int a_stages;             // halo-tile ring depth
+  int acc_bufs;             // 1 or 2 accumulator sets in TMEM
+  int acc_stride;           // TMEM columns per sub-tile accumulator (NT rounded up to 32)
+  int desc_mode;            // bit 0: put (start >> 7) & 7 into the descriptor's base-offset field
+};
+
+// Epilogue of output pixel (t, h, w), channels [n0, n0 + 32): rr = fp32 accumulators.
+// bias, bf16 rounding (the reference's bf16 conv output), residual add, store.
+__device__ __forceinline__ void conv_store_chunk(const ConvParams& p, const uint32_t* rr, int t, int h,
+                                                 int w, int n0) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(rr[i]);
+    if (p.bias != nullptr && n0 + i < p.Cout) v[i] += __bfloat162float(p.bias[n0 + i]);
+    v[i] = bf16_round(v[i]);
+  }
+  if (p.out_mode == 0) {
+    const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
+    const int ch = n0 % p.n_split;
+    const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
+    bf16* o = reinterpret_cast<bf16*>(p.out) + off;
+    const int nvalid = min(32, p.Cout - n0);
+    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      if (p.residual != nullptr) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+        uint4 u4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u4[q] = rp[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t ww[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[q * 8 + 2 * e] += __uint_as_float(ww[e] << 16);
+            v[q * 8 + 2 * e + 1] += __uint_as_float(ww[e] & 0xFFFF0000u);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        reinterpret_cast<uint4*>(o)[q] = u;
+      }
+    } else {
+      for (int i = 0; i < nvalid; ++i) {
+        float y = v[i];
+        if (p.residual != nullptr) y += __bfloat162float(p.residual[off + i]);
+        o[i] = __float2bfloat16_rn(y);
+      }
+    }
+  } else {
+    // planar NCTHW output of a few channels (decoder head / adaptor conv_out)
+    const long long pix = (static_cast<long long>(t) * p.H_out + h) * p.W_out + w;
+    for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
+      float y = v[i];
+      const long long off = (n0 + i) * p.planar_cstride + pix;
+      if (p.act == 1) y = fminf(1.f, fmaxf(-1.f, y));
+      if (p.act == 2) {
+        y = bf16_round(y + __bfloat162float(p.skip[off]));
+        y = 1.f / (1.f + __expf(-y));
+      }
+      reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// conv_halo.cu
+bool conv_halo_eligible(int Cin, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                        int T_in, int H_in, int W_in, int T_out, int H_out, int W_out);
+int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_packed, int Cout_pad,
+                     ConvParams p, cudaStream_t stream);
+
+}  // namespace m4d

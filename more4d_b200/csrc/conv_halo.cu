@@ -1,0 +1,332 @@
+// 3x3 (x kt) stride-1 convolution over channels-last activations with the input HALO staged once
+// in shared memory — the kernel behind CausalConv3d 3x3x3 (MoRe4D/models/wan_vae.py:21-40), the
+// 3x3 Conv2d's of Resample's upsample branch (:82-92) and of the adaptors' ResnetBlocks
+// (MoRe4D/models/trajectory_module.py:73-87): > 95 % of the Motion-Sensitive VAE's FLOPs.
+//
+// Why a second kernel: conv.cu issues one TMA box per tap, so every output tile pulls its input
+// window 27 times and its weights once per 128 pixels through L2; ncu shows it bound by the
+// L2->SM fabric (11.5 TB/s of TMA traffic, tensor pipe 43-47 %, profiles/conv_r01.md).  Here
+//   * one CTA tile is 16 x 16 output pixels of one frame = TWO M=128 sub-tiles that share every
+//     weight stage (weights stream once per 256 pixels), and
+//   * per time tap and 64-channel block ONE TMA box {64 ch, 18 w, 18 h} lands the haloed input
+//     window as [18][18] pixels x 128 B, SWIZZLE_128B; the nine spatial taps are nine UMMA
+//     descriptors into that same buffer: GEMM row m = (hh, ww) of a sub-tile is pixel
+//     (hh + b, ww + c + 8 sub) of the window, i.e. descriptor start = tap shift, 8-row groups =
+//     8 consecutive pixels of a row (128 B apart), stride between groups = one window row
+//     (18 * 128 B).  The 128-byte swizzle is a function of the shared-memory ADDRESS bits for
+//     both TMA and tcgen05.mma, so shifted starts read back exactly what TMA wrote.
+// L2->SM traffic per output pixel drops ~3.3x for 96->96 channels (1134 KB / 128 px ->
+// 673 KB / 256 px) and more for wider layers.  Zero padding in space and the causal padding in
+// time are TMA out-of-bounds zero fill (negative box coordinates), as in conv.cu.
+//
+// CTA = 384 threads, persistent: warp 0 halo producer, warp 3 weight producer, warp 1 MMA
+// issuer, warp 2 TMEM allocator, warps 4-7 / 8-11 epilogue of sub-tile 0 / 1.  Accumulators:
+// 2 sub-tiles x NT columns, double-buffered when 4 * NT <= 512.
+#include "conv_common.cuh"
+
+namespace m4d {
+
+constexpr int CH_T = 16;                         // output tile is CH_T x CH_T pixels
+constexpr int CH_HW = CH_T + 2;                  // haloed window edge
+constexpr int CH_A_BYTES = CH_HW * CH_HW * 128;  // 41472: [18][18] pixels x 64 channels
+constexpr int CH_A_STRIDE = 41 * 1024;           // ring stride (1024-B aligned for SWIZZLE_128B)
+constexpr int CH_ROW_BYTES = CH_HW * 128;        // one window row = stride between 8-pixel groups
+constexpr int CH_THREADS = 384;
+constexpr int CH_MAX_A = 3, CH_MAX_B = 8;
+constexpr int CH_SMEM_MAX = 227 * 1024;
+
+// SWIZZLE_128B K-major descriptors as {lo, hi}: lo = (address >> 4) | LBO(16 B) << 16, hi = SBO >> 4 |
+// version 1 | layout SWIZZLE_128B.  The base-offset field stays 0 although tap-shifted starts are
+// not 1024-B aligned: measured on the B200, the swizzle XOR is taken from the absolute address
+// bits (a non-zero base offset gives wrong results), matching what TMA wrote.
+constexpr uint32_t CH_DESC_HI_A = (CH_ROW_BYTES >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t CH_DESC_HI_B = (1024 >> 4) | (1u << 14) | (2u << 29);
+
+__device__ __forceinline__ uint64_t desc_pair(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// All MMAs of one spatial tap: both sub-tiles x KS k-slices of 16 channels.
+template <int KS>
+__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b_lo,
+                                          uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    umma_ss(d0, desc_pair(a_lo + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc,
+            k == 0 ? acc0 : 1u);
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    umma_ss(d1, desc_pair(a_lo + 64 + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc,
+            k == 0 ? acc0 : 1u);
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int b_bytes = p.NT * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.a_stages * CH_A_STRIDE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + p.stages * b_bytes);
+  uint64_t* a_empty = a_full + CH_MAX_A;
+  uint64_t* b_full = a_empty + CH_MAX_A;
+  uint64_t* b_empty = b_full + CH_MAX_B;
+  uint64_t* tfull = b_empty + CH_MAX_B;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == 3 && lane == 0) tma_prefetch_desc(&tmW);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CH_MAX_A; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < CH_MAX_B; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);                  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_w = (p.W_out + CH_T - 1) / CH_T;
+  const int tiles_h = (p.H_out + CH_T - 1) / CH_T;
+  const int tiles = p.T_out * tiles_h * tiles_w * p.n_tiles;
+  const int cblocks = (p.Cin + 63) / 64;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ halo producer
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int r = tile / p.n_tiles;
+        const int w_blk = r % tiles_w; r /= tiles_w;
+        const int h_blk = r % tiles_h;
+        const int t = r / tiles_h;
+        for (int a = 0; a < p.kt; ++a)
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&a_full[sa], CH_A_BYTES);
+            tma_load_4d(sA + sa * CH_A_STRIDE, &tmX, &a_full[sa], cb * 64, w_blk * CH_T - 1,
+                        h_blk * CH_T - 1, t + a - p.pt);
+            if (++sa == p.a_stages) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        for (int a = 0; a < p.kt; ++a)
+          for (int cb = 0; cb < cblocks; ++cb)
+            for (int tap9 = 0; tap9 < 9; ++tap9) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+              tma_load_2d(sB + sb * b_bytes, &tmW, &b_full[sb], (a * 9 + tap9) * p.Cin + cb * 64,
+                          n_blk * p.NT);
+              if (++sb == p.stages) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp runs the loops converged (operands stay in uniform registers); one
+    // elected lane issues.  Descriptors are {lo, hi} pairs whose hi word is constant and whose
+    // lo word only takes compile-time offsets per (tap, sub-tile, k-slice): the issue rate of
+    // this thread bounds the N = 96 layers (48 clk per MMA).
+    const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int acc = it % p.acc_bufs;
+      const uint32_t acc_phase = (it / p.acc_bufs) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 2 * p.acc_stride;
+      const uint32_t d_tmem1 = d_tmem + p.acc_stride;
+      for (int a = 0; a < p.kt; ++a)
+        for (int cb = 0; cb < cblocks; ++cb) {
+          const int ch_left = p.Cin - cb * 64;
+          const int kslices = ch_left >= 64 ? 4 : (ch_left >> 4);
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_lo = (((a_base + sa * CH_A_STRIDE) >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+          for (int tap9 = 0; tap9 < 9; ++tap9) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_lo = (((b_base + sb * b_bytes) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3)) * 8;
+            const uint32_t acc0 = (a | cb | tap9) == 0 ? 0u : 1u;
+            if (elect_one()) {
+              if (kslices == 4) {
+                issue_tap<4>(d_tmem, d_tmem1, a_tap, b_lo, idesc, acc0);
+              } else if (kslices == 2) {
+                issue_tap<2>(d_tmem, d_tmem1, a_tap, b_lo, idesc, acc0);
+              } else {
+                for (int k = 0; k < kslices; ++k) {
+                  umma_ss(d_tmem, desc_pair(a_tap + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B),
+                          idesc, acc0 | (k != 0));
+                  umma_ss(d_tmem1, desc_pair(a_tap + 64 + 2 * k, CH_DESC_HI_A),
+                          desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc, acc0 | (k != 0));
+                }
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (++sb == p.stages) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+          if (++sa == p.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int sub = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      int r = tile;
+      const int n_blk = r % p.n_tiles; r /= p.n_tiles;
+      const int w_blk = r % tiles_w; r /= tiles_w;
+      const int h_blk = r % tiles_h;
+      const int t = r / tiles_h;
+      const int h = h_blk * CH_T + (m >> 3);
+      const int w = w_blk * CH_T + sub * 8 + (m & 7);
+      const bool pix_ok = (h < p.H_out) && (w < p.W_out);
+      const int acc = it % p.acc_bufs;
+      const uint32_t acc_phase = (it / p.acc_bufs) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             acc * 2 * p.acc_stride + sub * p.acc_stride;
+      for (int c0 = 0; c0 < p.NT; c0 += 32) {
+        const int n0 = n_blk * p.NT + c0;
+        if (n0 >= p.Cout) break;                       // warp-uniform
+        uint32_t rr[32];
+        tmem_ld32(t_row + c0, rr);
+        tmem_ld_wait();
+        if (!pix_ok) continue;
+        conv_store_chunk(p, rr, t, h, w, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+bool conv_halo_eligible(int Cin, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                        int T_in, int H_in, int W_in, int T_out, int H_out, int W_out) {
+  (void)T_in; (void)T_out; (void)pt;
+  return kh == 3 && kw == 3 && (kt == 1 || kt == 3) && st == 1 && sh == 1 && sw == 1 && ph == 1 &&
+         pw == 1 && Cin % 32 == 0 && H_out == H_in && W_out == W_in;
+}
+
+int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_packed, int Cout_pad,
+                     ConvParams p, cudaStream_t stream) {
+  int NT = 16;
+  for (int cand = 256; cand >= 16; cand -= 16)
+    if (Cout_pad % cand == 0) { NT = cand; break; }
+  p.NT = NT;
+  p.n_tiles = Cout_pad / NT;
+  p.acc_stride = (NT + 31) & ~31;
+  p.acc_bufs = (4 * p.acc_stride <= 512) ? 2 : 1;
+  p.desc_mode = 0;
+  const int b_bytes = NT * 128;
+  const int fixed = 1024 + 512;                         // alignment slack + barriers
+  p.a_stages = 2;
+  int stages = (CH_SMEM_MAX - fixed - p.a_stages * CH_A_STRIDE) / b_bytes;
+  if ((CH_SMEM_MAX - fixed - 3 * CH_A_STRIDE) / b_bytes >= 6) {
+    p.a_stages = 3;
+    stages = (CH_SMEM_MAX - fixed - 3 * CH_A_STRIDE) / b_bytes;
+  }
+  p.stages = stages > CH_MAX_B ? CH_MAX_B : stages;
+  M4D_REQUIRE(p.stages >= 3, M4D_ERR_UNSUPPORTED);
+
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return M4D_ERR_NO_DEVICE;
+  if (!aligned16(x) || !aligned16(w_packed)) return M4D_ERR_ALIGN;
+  CUtensorMap tmX, tmW;
+  {
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(W_in),
+                          static_cast<cuuint64_t>(H_in), static_cast<cuuint64_t>(T_in)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.Cin) * 2, static_cast<cuuint64_t>(W_in) * p.Cin * 2,
+                          static_cast<cuuint64_t>(H_in) * W_in * p.Cin * 2};
+    cuuint32_t box[4] = {64, CH_HW, CH_HW, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[more4d_b200] conv_halo: cuTensorMapEncodeTiled(X) failed: %d\n", static_cast<int>(r));
+      return M4D_ERR_CUDA;
+    }
+    const long long Ktot = static_cast<long long>(p.kt) * 9 * p.Cin;
+    cuuint64_t wdim[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Cout_pad)};
+    cuuint64_t wstr[1] = {static_cast<cuuint64_t>(Ktot) * 2};
+    cuuint32_t wbox[2] = {64, static_cast<cuuint32_t>(NT)};
+    cuuint32_t wes[2] = {1, 1};
+    r = fn(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), wdim, wstr, wbox, wes,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[more4d_b200] conv_halo: cuTensorMapEncodeTiled(W) failed: %d\n", static_cast<int>(r));
+      return M4D_ERR_CUDA;
+    }
+  }
+  const int smem_bytes = p.a_stages * CH_A_STRIDE + p.stages * b_bytes + fixed;
+  static bool configured = false;
+  if (!configured) {
+    int rc = cuda_ok(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          CH_SMEM_MAX),
+                     "cudaFuncSetAttribute(conv_halo)");
+    if (rc != M4D_OK) return rc;
+    configured = true;
+  }
+  const long long tiles = static_cast<long long>(p.T_out) * ((p.H_out + CH_T - 1) / CH_T) *
+                          ((p.W_out + CH_T - 1) / CH_T) * p.n_tiles;
+  M4D_REQUIRE(tiles < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  const int grid = tiles < sm_count() ? static_cast<int>(tiles) : sm_count();
+  conv_halo_kernel<<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
+  M4D_CHECK_LAUNCH("conv_halo_kernel");
+  return M4D_OK;
+}
+
+}  // namespace m4d

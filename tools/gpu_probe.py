@@ -209,6 +209,59 @@ def attn_sweep():
     _lib.lib().m4d_set_debug_flags(0)
 
 
+def conv():
+    """Halo-staging conv kernel vs the per-tap kernel (debug flag 0x10000) and the oracle; the
+    descriptor base-offset variant (0x20000); then timing at the VAE's dominant shapes."""
+    from oracle import vae_oracle as V
+    ar = V.Arith(True)
+    L = _lib.lib()
+
+    def cl(x):
+        return x[0].permute(1, 2, 3, 0).contiguous().cuda()
+
+    def ncthw(y):
+        return y.permute(3, 0, 1, 2).unsqueeze(0).float().cpu()
+
+    for (cin, cout, T, H, W, kt) in [(64, 64, 1, 16, 16, 1), (64, 64, 2, 20, 40, 3), (96, 96, 3, 12, 20, 3),
+                                     (32, 192, 2, 8, 16, 3), (192, 384, 2, 9, 17, 3), (128, 128, 2, 33, 47, 1)]:
+        x = rnd((1, cin, T, H, W), 1)
+        w = rnd((cout, cin, kt, 3, 3), 2, (cin * 9 * kt) ** -0.5)
+        b = rnd((cout,), 3, 0.1)
+        if kt == 3:
+            ref = V.causal_conv3d(x.float(), w, b, ar)
+        else:
+            ref = V.conv2d_frames(x.float(), w[:, :, 0], b, ar, stride=1, pad=(1, 1, 1, 1))
+        wp = ops.pack_conv_weight(w.cuda())
+        for flags, name in ((0x10000, "per-tap"), (0, "halo"), (0x20000, "halo+base_offset")):
+            L.m4d_set_debug_flags(flags)
+            y = ops.conv_cl(cl(x), wp, b.cuda(), cout, (kt, 3, 3), pad=(kt - 1, 1, 1))
+            torch.cuda.synchronize()
+            print(f"conv {cin}->{cout} T{T} {H}x{W} kt{kt} [{name}]: rel={rel(ncthw(y), ref):.3e}", flush=True)
+    L.m4d_set_debug_flags(0)
+    for (cin, cout, T, H, W) in [(96, 96, 8, 720, 1280), (192, 192, 8, 360, 640), (384, 384, 8, 180, 320),
+                                 (384, 384, 13, 90, 160), (128, 128, 8, 720, 1280)]:
+        kt = 1 if cin == 128 else 3
+        x = torch.randn(T, H, W, cin, device="cuda", dtype=BF16)
+        w = torch.randn(cout, cin, kt, 3, 3, device="cuda", dtype=BF16) * 0.02
+        wp = ops.pack_conv_weight(w)
+        out = torch.empty(T, H, W, cout, device="cuda", dtype=BF16)
+        fl = 2.0 * T * H * W * cin * cout * 9 * kt
+        for flags, name in ((0x10000, "per-tap"), (0, "halo"), (0x20000, "halo+bo")):
+            L.m4d_set_debug_flags(flags)
+            for _ in range(2):
+                ops.conv_cl(x, wp, None, cout, (kt, 3, 3), pad=(kt - 1, 1, 1), out=out)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+                s_.record(); ops.conv_cl(x, wp, None, cout, (kt, 3, 3), pad=(kt - 1, 1, 1), out=out); e_.record()
+                torch.cuda.synchronize()
+                ts.append(s_.elapsed_time(e_))
+            ms = min(ts)
+            print(f"conv {cin}->{cout} T{T} {H}x{W} kt{kt} [{name}]: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+    L.m4d_set_debug_flags(0)
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep, "gemm_shapes": gemm_shapes, "gemm2": gemm2, "gemm2_k": gemm2_k}[sys.argv[1]]()
+    {"gemm": gemm, "attn": attn, "attn_sweep": attn_sweep, "gemm_shapes": gemm_shapes, "gemm2": gemm2, "gemm2_k": gemm2_k, "conv": conv}[sys.argv[1]]()
