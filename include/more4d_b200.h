@@ -150,6 +150,18 @@ int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin, const void
                 int out_C, int t_mul, int t_off, int n_split, const void* residual, int out_mode,
                 int act, const void* skip, void* stream);
 
+/* The 3x3 (x kt, causal) stride-1 case of m4d_conv_cl with the CONSUMER's RMS_norm [+ SiLU] fused
+ * into the epilogue: ResidualBlock = [RMS_norm, SiLU, conv, RMS_norm, SiLU, conv] + shortcut
+ * (wan_vae.py:198-202,206-224), so each conv's output is immediately normalised over channels
+ * (wan_vae.py:43-58).  Cout in {96, 192} (one epilogue thread owns a whole pixel); x bf16
+ * [T, H, W, Cin]; residual (or NULL) is added to the conv output first.  Writes
+ *   out      [T, H, W, Cout] = conv (+ residual)            — or skipped when out == NULL
+ *   norm_out [T, H, W, Cout] = [SiLU](RMS_norm(out) * gamma), same rounding points as
+ *                              m4d_rmsnorm_silu_cl applied to `out`. */
+int m4d_conv3x3_rmsnorm_cl(const void* x, int T, int H, int W, int Cin, const void* w_packed, int Cout,
+                           const void* bias, int kt, void* out, const void* residual,
+                           const void* gamma, void* norm_out, int do_silu, void* stream);
+
 /* Direct conv for 3-channel planar inputs x bf16 [3, T, H, W] -> channels-last [T, H, W, Cout]:
  * Encoder3d.conv1 (wan_vae.py:289, kt = 3 causal) and the adaptors' conv_in
  * (trajectory_module.py:142, kt = 1); weights in the reference layout [Cout, 3, kt, 3, 3].

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "m4d_silu_bf16": (c_int, [_P, _P, _L, _P]),
     "m4d_conv_cl": (c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P] + [_I] * 12 + [_P, _I, _I, _I, _I, _P,
                             _I, _I, _P, _P]),
+    "m4d_conv3x3_rmsnorm_cl": (c_int, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
     "m4d_conv_in3": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
     "m4d_rmsnorm_silu_cl": (c_int, [_P, _P, _P, _L, _I, _I, _P]),
     "m4d_upsample2x_cl": (c_int, [_P, _P, _I, _I, _I, _I, _P]),

@@ -40,6 +40,7 @@ constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024;
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
 constexpr int A_DEFAULT_VAR = 0;
 constexpr int A_DEFAULT_K64 = 0;              // 1: use the double-buffered 64-key-step kernel
+constexpr int A_DEFAULT_PACE = 0;             // FFMA2 pacing distance in pairs (exp_pairs)
 constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe (measured: 0 is fastest)
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -89,21 +90,39 @@ __device__ __forceinline__ void ex2_emul2(float x0, float x1, float& r0, float& 
   r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
+// c + 0 * dep: the value of c, but data-dependent on `dep` (ptxas cannot fold an IEEE 0 * x).
+__device__ __forceinline__ float pace_after(float dep, float c) {
+  float r;
+  asm("fma.rn.f32 %0, %1, 0f00000000, %2;" : "=f"(r) : "f"(dep), "f"(c));
+  return r;
+}
+
 // p = 2^(s*c + neg_mc) for 64 logits -> 32 packed bf16x2 registers; PP of every 8 pairs use the
 // polynomial path.  Row-sum partials are accumulated pairwise (FADD2).
-template <int PP, int Q0, int Q1>
+//
+// Pacing: the MUFU issues one warp-wide EX2 per 8 clocks, so a row's 128 exponentials take
+// >= 1024 clocks and everything else (FFMA2 scale, FADD2 sum, bf16 pack) fits in the gaps — but
+// only if it is interleaved.  Left alone, ptxas hoists all independent FFMA2s to the front and
+// leaves a bare MUFU tail (profiles/attn_r01c: 64 x [EX2, EX2, FADD2, F2FP] = 1275 of the 1760
+// busy clocks per tile).  With PACE > 0 the scale operand of pair q is made data-dependent on
+// the EX2 result of pair q - PACE, which pins each FFMA2 into the gap after that EX2.
+template <int PP, int Q0, int Q1, int PACE>
 __device__ __forceinline__ void exp_pairs(const uint32_t* s, uint32_t* pk, float c, float neg_mc,
                                           float& l0, float& l1) {
+  float hist[Q1 - Q0];
 #pragma unroll
   for (int q = Q0; q < Q1; ++q) {
     float x0, x1, p0, p1;
-    fma2(x0, x1, __uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1]), c, c, neg_mc, neg_mc);
+    float cq = c;
+    if (PACE > 0 && q - Q0 >= PACE) cq = pace_after(hist[q - Q0 - PACE], c);
+    fma2(x0, x1, __uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1]), cq, cq, neg_mc, neg_mc);
     if ((q & 7) >= 8 - PP) {
       ex2_emul2(x0, x1, p0, p1);
     } else {
       p0 = fast_exp2(x0);
       p1 = fast_exp2(x1);
     }
+    hist[q - Q0] = p1;
     add2(l0, l1, p0, p1);
     pk[q] = pack_bf16(p0, p1);
   }
@@ -125,7 +144,7 @@ struct AttnParams {
 // (-4 %), loading the second half of S while max-reducing the first (-1 %), polynomial exp2 on
 // the FMA pipe for 12-50 % of the logits (PP > 0: -4 .. -11 %, the softmax is latency-, not
 // MUFU-bound), and the double-buffered 64-key-step kernel below (-25 %).
-template <int PP, int VAR>
+template <int PP, int VAR, int PACE>
 __global__ void __launch_bounds__(A_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -381,7 +400,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
           uint32_t pq[16];
-          exp_pairs<PP, 0, 16>(s + sl * 32, pq, c, neg_mc, l0, l1);
+          exp_pairs<PP, 0, 16, PACE>(s + sl * 32, pq, c, neg_mc, l0, l1);
           tmem_st16(tS + sl * 16, pq);
           tmem_st_wait();
           tc_fence_before();
@@ -389,9 +408,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       } else if (VAR == 2) {
         uint32_t pa[32], pb[32];
-        exp_pairs<PP, 0, 32>(s, pa, c, neg_mc, l0, l1);
+        exp_pairs<PP, 0, 32, PACE>(s, pa, c, neg_mc, l0, l1);
         tmem_st32(tS, pa);
-        exp_pairs<PP, 0, 32>(s + 64, pb, c, neg_mc, l0, l1);
+        exp_pairs<PP, 0, 32, PACE>(s + 64, pb, c, neg_mc, l0, l1);
         tmem_st32(tS + 32, pb);
         tmem_st_wait();
         tc_fence_before();
@@ -400,7 +419,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
           uint32_t ph[32];
-          exp_pairs<PP, 0, 32>(s + sl * 64, ph, c, neg_mc, l0, l1);
+          exp_pairs<PP, 0, 32, PACE>(s + sl * 64, ph, c, neg_mc, l0, l1);
           tmem_st32(tS + sl * 32, ph);
           tmem_st_wait();
           tc_fence_before();
@@ -693,7 +712,7 @@ attn_fwd_d128_k64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const float neg_mc = -m_used * c;
       float l0 = 0.f, l1 = 0.f;
       uint32_t pk[32];
-      exp_pairs<0, 0, 32>(s, pk, c, neg_mc, l0, l1);
+      exp_pairs<0, 0, 32, 0>(s, pk, c, neg_mc, l0, l1);
       tmem_st32(tS, pk);
       l_sum += l0 + l1;
       tmem_st_wait();
@@ -789,8 +808,18 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
     var = g_debug_flags & 0x7;
   }
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = nullptr;
-  if (pp == 0) kern = var == 1 ? attn_fwd_d128_kernel<0, 1> : (var == 2 ? attn_fwd_d128_kernel<0, 2> : attn_fwd_d128_kernel<0, 0>);
-  else if (pp == 2) kern = (var & 1) ? attn_fwd_d128_kernel<2, 1> : attn_fwd_d128_kernel<2, 0>;
+  // debug flags 0x1000000 | (PACE << 20): pacing distance variant (0, 2, 4, 6)
+  int pace = A_DEFAULT_PACE;
+  if (g_debug_flags & 0x1000000) pace = (g_debug_flags >> 20) & 0xF;
+  if (pp == 0 && var == 0) {
+    kern = pace == 0 ? attn_fwd_d128_kernel<0, 0, 0>
+         : pace == 2 ? attn_fwd_d128_kernel<0, 0, 2>
+         : pace == 6 ? attn_fwd_d128_kernel<0, 0, 6> : attn_fwd_d128_kernel<0, 0, 4>;
+  } else if (pp == 0) {
+    kern = var == 1 ? attn_fwd_d128_kernel<0, 1, 0> : attn_fwd_d128_kernel<0, 2, 0>;
+  } else if (pp == 2) {
+    kern = (var & 1) ? attn_fwd_d128_kernel<2, 1, 0> : (pace ? attn_fwd_d128_kernel<2, 0, 4> : attn_fwd_d128_kernel<2, 0, 0>);
+  }
   int smem_bytes = A_SMEM_BYTES;
   if (k64) {
     kern = attn_fwd_d128_k64_kernel;

@@ -246,14 +246,14 @@ conv_in3_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf
 
 using namespace m4d;
 
-extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin, const void* w_packed,
-                           int Cout, int Cout_pad, const void* bias, int kt, int kh, int kw, int st,
-                           int sh, int sw, int pt, int ph, int pw, int T_out, int H_out, int W_out,
-                           void* out, int out_C, int t_mul, int t_off, int n_split,
-                           const void* residual, int out_mode, int act, const void* skip,
-                           void* stream_) {
+static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, const void* w_packed,
+                        int Cout, int Cout_pad, const void* bias, int kt, int kh, int kw, int st,
+                        int sh, int sw, int pt, int ph, int pw, int T_out, int H_out, int W_out,
+                        void* out, int out_C, int t_mul, int t_off, int n_split,
+                        const void* residual, int out_mode, int act, const void* skip,
+                        const void* norm_gamma, void* norm_out, int norm_silu, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  M4D_REQUIRE(x && w_packed && out, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(x && w_packed && (out || norm_out), M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(T_in > 0 && H_in > 0 && W_in > 0 && T_out > 0 && H_out > 0 && W_out > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(Cin > 0 && Cin % CV_KB == 0, M4D_ERR_UNSUPPORTED);
   M4D_REQUIRE(Cout > 0 && Cout_pad >= Cout && Cout_pad % 16 == 0, M4D_ERR_UNSUPPORTED);
@@ -288,12 +288,16 @@ extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin,
   p.skip = static_cast<const bf16*>(skip);
   p.planar_cstride = static_cast<long long>(T_out) * H_out * W_out;
   p.a_stages = 0; p.acc_bufs = 0; p.acc_stride = 0; p.desc_mode = 0;
+  p.norm_gamma = static_cast<const bf16*>(norm_gamma);
+  p.norm_out = static_cast<bf16*>(norm_out);
+  p.norm_silu = norm_silu;
 
   // 3x3 (x kt) stride-1 convolutions — almost all of the VAE's FLOPs — take the halo-staging
   // kernel (conv_halo.cu); debug flag 0x10000 forces the per-tap kernel below.
   if (!(g_debug_flags & 0x10000) &&
       conv_halo_eligible(Cin, kt, kh, kw, st, sh, sw, pt, ph, pw, T_in, H_in, W_in, T_out, H_out, W_out))
     return conv_halo_launch(x, T_in, H_in, W_in, w_packed, Cout_pad, p, stream);
+  M4D_REQUIRE(norm_out == nullptr, M4D_ERR_UNSUPPORTED);      // the fused norm lives in conv_halo.cu
 
   CUtensorMap tmX, tmW;
   {
@@ -343,6 +347,26 @@ extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin,
   conv_cl_kernel<<<grid, CV_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
   M4D_CHECK_LAUNCH("conv_cl_kernel");
   return M4D_OK;
+}
+
+extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin, const void* w_packed,
+                           int Cout, int Cout_pad, const void* bias, int kt, int kh, int kw, int st,
+                           int sh, int sw, int pt, int ph, int pw, int T_out, int H_out, int W_out,
+                           void* out, int out_C, int t_mul, int t_off, int n_split,
+                           const void* residual, int out_mode, int act, const void* skip,
+                           void* stream_) {
+  return conv_cl_impl(x, T_in, H_in, W_in, Cin, w_packed, Cout, Cout_pad, bias, kt, kh, kw, st, sh, sw, pt,
+                      ph, pw, T_out, H_out, W_out, out, out_C, t_mul, t_off, n_split, residual, out_mode,
+                      act, skip, nullptr, nullptr, 0, stream_);
+}
+
+extern "C" int m4d_conv3x3_rmsnorm_cl(const void* x, int T, int H, int W, int Cin, const void* w_packed,
+                                      int Cout, const void* bias, int kt, void* out, const void* residual,
+                                      const void* gamma, void* norm_out, int do_silu, void* stream_) {
+  M4D_REQUIRE(gamma && norm_out && (kt == 1 || kt == 3), M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(Cout == 96 || Cout == 192, M4D_ERR_UNSUPPORTED);
+  return conv_cl_impl(x, T, H, W, Cin, w_packed, Cout, Cout, bias, kt, 3, 3, 1, 1, 1, kt - 1, 1, 1, T, H, W,
+                      out, Cout, 1, 0, Cout, residual, 0, 0, nullptr, gamma, norm_out, do_silu, stream_);
 }
 
 extern "C" int m4d_conv_in3(const void* x, const void* w, const void* bias, void* out, int T, int H,

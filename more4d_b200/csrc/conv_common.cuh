@@ -29,8 +29,62 @@ struct ConvParams {
   int a_stages;             // halo-tile ring depth
   int acc_bufs;             // 1 or 2 accumulator sets in TMEM
   int acc_stride;           // TMEM columns per sub-tile accumulator (NT rounded up to 32)
-  int desc_mode;            // bit 0: put (start >> 7) & 7 into the descriptor's base-offset field
+  int desc_mode;            // unused (kept 0): see the base-offset note in conv_halo.cu
+  // fused RMS_norm (+ SiLU) of the conv output (conv_halo.cu, NT == Cout in {96, 192}):
+  // norm_out = [silu](rms_norm(y) * gamma), same NHWC addressing as `out`; `out` may be null
+  // when only the normalised tensor is consumed (ResidualBlock conv1 -> norm2, vae:198-202)
+  const bf16* norm_gamma;
+  bf16* norm_out;
+  int norm_silu;
 };
+
+// SiLU on a bf16-rounded input, result rounded to bf16 (reference: nn.SiLU on a bf16 tensor).
+// __fdividef / __expf: the <= 2 ulp fp32 error is invisible after the bf16 rounding.
+__device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(__fdividef(x, 1.f + __expf(-x))); }
+
+// Final bf16 values (as floats) of output pixel (t, h, w), channels [n0, n0 + 32), NHWC mode with
+// all 32 channels valid: bias, bf16 rounding (the reference's bf16 conv output), residual add
+// (ResidualBlock, vae:224) and its rounding.  Returns the element offset of the chunk.
+__device__ __forceinline__ long long conv_chunk_values(const ConvParams& p, const uint32_t* rr, int t,
+                                                       int h, int w, int n0, float* v, bool pix_ok) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(rr[i]);
+    if (p.bias != nullptr) v[i] += __bfloat162float(p.bias[n0 + i]);
+    v[i] = bf16_round(v[i]);
+  }
+  const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
+  const int ch = n0 % p.n_split;
+  const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
+  if (p.residual != nullptr && pix_ok) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+    uint4 u4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u4[q] = rp[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t ww[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[q * 8 + 2 * e] = bf16_round(v[q * 8 + 2 * e] + __uint_as_float(ww[e] << 16));
+        v[q * 8 + 2 * e + 1] = bf16_round(v[q * 8 + 2 * e + 1] + __uint_as_float(ww[e] & 0xFFFF0000u));
+      }
+    }
+  }
+  return off;
+}
+
+__device__ __forceinline__ void store_chunk_bf16(bf16* o, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    reinterpret_cast<uint4*>(o)[q] = u;
+  }
+}
 
 // Epilogue of output pixel (t, h, w), channels [n0, n0 + 32): rr = fp32 accumulators.
 // bias, bf16 rounding (the reference's bf16 conv output), residual add, store.

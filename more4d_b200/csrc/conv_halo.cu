@@ -60,6 +60,59 @@ __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_l
             k == 0 ? acc0 : 1u);
 }
 
+// Epilogue with the NEXT layer's RMS_norm (+ SiLU) fused in (wan_vae.py:43-58 after :198-202):
+// the thread owns all NTC = Cout channels of its pixel, so the L2 norm over channels is a
+// thread-local reduction.  Same rounding points as rmsnorm_silu_cl_kernel: norm rounded to
+// bf16, then y / norm, * sqrt(C), * gamma, SiLU each rounded to bf16.  Writes the raw output
+// (when p.out != null) and the normalised one; removes one read + one write of the activation
+// and a kernel launch per RMS_norm.
+template <int NTC>
+__device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t_row, int t, int h, int w,
+                                                 bool pix_ok) {
+  uint32_t yp[NTC / 2];
+  float ss = 0.f;
+  long long off0 = 0;
+#pragma unroll
+  for (int c0 = 0; c0 < NTC; c0 += 32) {
+    uint32_t rr[32];
+    tmem_ld32(t_row + c0, rr);
+    tmem_ld_wait();
+    float v[32];
+    const long long off = conv_chunk_values(p, rr, t, h, w, c0, v, pix_ok);
+    if (c0 == 0) off0 = off;
+    if (p.out != nullptr && pix_ok) store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + off, v);
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      ss += v[i] * v[i] + v[i + 1] * v[i + 1];
+      yp[(c0 + i) >> 1] = pack_bf16(v[i], v[i + 1]);
+    }
+  }
+  if (!pix_ok) return;
+  const float inv = 1.0f / fmaxf(bf16_round(sqrtf(ss)), 1e-12f);
+  const float sc = sqrtf(static_cast<float>(NTC));
+  bf16* o = p.norm_out + off0;
+#pragma unroll
+  for (int c0 = 0; c0 < NTC; c0 += 8) {
+    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.norm_gamma + c0));
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t yw = yp[(c0 >> 1) + e];
+      float a = __uint_as_float(yw << 16), b = __uint_as_float(yw & 0xFFFF0000u);
+      const float ga = __uint_as_float(gw[e] << 16), gb = __uint_as_float(gw[e] & 0xFFFF0000u);
+      a = bf16_round(bf16_round(bf16_round(a * inv) * sc) * ga);
+      b = bf16_round(bf16_round(bf16_round(b * inv) * sc) * gb);
+      if (p.norm_silu) {
+        a = silu_bf16r(a);
+        b = silu_bf16r(b);
+      }
+      ow[e] = pack_bf16(a, b);
+    }
+    *reinterpret_cast<uint4*>(o + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  ConvParams p) {
@@ -233,14 +286,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              acc * 2 * p.acc_stride + sub * p.acc_stride;
-      for (int c0 = 0; c0 < p.NT; c0 += 32) {
-        const int n0 = n_blk * p.NT + c0;
-        if (n0 >= p.Cout) break;                       // warp-uniform
-        uint32_t rr[32];
-        tmem_ld32(t_row + c0, rr);
-        tmem_ld_wait();
-        if (!pix_ok) continue;
-        conv_store_chunk(p, rr, t, h, w, n0);
+      if (p.norm_out != nullptr) {                     // NT == Cout in {96, 192}, checked on the host
+        if (p.NT == 96) epilogue_rmsnorm<96>(p, t_row, t, h, w, pix_ok);
+        else epilogue_rmsnorm<192>(p, t_row, t, h, w, pix_ok);
+      } else {
+        for (int c0 = 0; c0 < p.NT; c0 += 32) {
+          const int n0 = n_blk * p.NT + c0;
+          if (n0 >= p.Cout) break;                     // warp-uniform
+          uint32_t rr[32];
+          tmem_ld32(t_row + c0, rr);
+          tmem_ld_wait();
+          if (!pix_ok) continue;
+          conv_store_chunk(p, rr, t, h, w, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -269,6 +327,14 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   p.acc_stride = (NT + 31) & ~31;
   p.acc_bufs = (4 * p.acc_stride <= 512) ? 2 : 1;
   p.desc_mode = 0;
+  if (p.norm_out != nullptr) {
+    M4D_REQUIRE(p.norm_gamma != nullptr && p.out_mode == 0 && p.n_tiles == 1 && NT == p.Cout &&
+                    (NT == 96 || NT == 192) && p.n_split >= p.Cout && p.out_C % 8 == 0,
+                M4D_ERR_UNSUPPORTED);
+    M4D_REQUIRE(aligned16(p.norm_out) && aligned16(p.norm_gamma) && (p.out == nullptr || aligned16(p.out)) &&
+                    (p.residual == nullptr || aligned16(p.residual)),
+                M4D_ERR_ALIGN);
+  }
   const int b_bytes = NT * 128;
   const int fixed = 1024 + 512;                         // alignment slack + barriers
   p.a_stages = 2;

@@ -353,6 +353,30 @@ def conv_cl(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kern
     return out_t
 
 
+def conv3x3_rmsnorm_cl(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kt: int,
+                       gamma: Tensor, silu: bool = True, want_raw: bool = True,
+                       residual: Optional[Tensor] = None):
+    """3x3 (x kt causal) stride-1 conv whose epilogue also emits RMS_norm[+SiLU] of its output
+    (the next layer's first op).  Returns (raw or None, normalised), both [T, H, W, cout]."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    if not x.is_contiguous():
+        raise ValueError("more4d_b200.conv3x3_rmsnorm_cl: x must be contiguous [T, H, W, C]")
+    T, H, W, Cin = x.shape
+    if w_packed.shape != (cout, kt * 9 * Cin):
+        raise ValueError("more4d_b200.conv3x3_rmsnorm_cl: packed weight does not match (cout, taps, Cin)")
+    raw = torch.empty(T, H, W, cout, device=x.device, dtype=BF16) if want_raw else None
+    normed = torch.empty(T, H, W, cout, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_conv3x3_rmsnorm_cl(
+        x.data_ptr(), T, H, W, Cin, w_packed.data_ptr(), cout, _ptr(bias), kt, _ptr(raw), _ptr(residual),
+        gamma.data_ptr(), normed.data_ptr(), int(silu), _stream())
+    _lib.check(rc, "m4d_conv3x3_rmsnorm_cl")
+    return raw, normed
+
+
+FUSED_NORM_CHANNELS = (96, 192)     # Cout values m4d_conv3x3_rmsnorm_cl supports
+
+
 def conv_in3(x_planar: Tensor, w: Tensor, bias: Optional[Tensor], kt: int, in_scale: float = 1.0,
              in_shift: float = 0.0) -> Tensor:
     """x [3, T, H, W] planar bf16 -> channels-last [T, H, W, Cout] (causal in time for kt = 3)."""

@@ -124,6 +124,7 @@ class AutoencoderKLWan(nn.Module):
         self.scale = [self.mean, 1.0 / self.std]
         self._packed = _PackedWeights()
         self._consts = None
+        self.fuse_norms = True      # RMS_norm+SiLU in the producing conv's epilogue (96/192 channels)
 
     @property
     def dtype(self):
@@ -160,13 +161,32 @@ class AutoencoderKLWan(nn.Module):
         w = self._p(name + ".weight")
         return ops.conv_cl(x, self._packed.get(name, w), self._p(name + ".bias"), cout, kernel, pad=pad, **kw)
 
-    def _res(self, x: Tensor, name: str, cin: int, cout: int) -> Tensor:
+    def _conv_norm(self, x: Tensor, name: str, kt: int, cout: int, gamma: Tensor, want_raw: bool = True,
+                   residual: Optional[Tensor] = None):
+        """3x3 conv whose epilogue also emits [SiLU](RMS_norm(out) * gamma) — the consumer's first
+        op (vae:198-202) — for the channel counts the fused epilogue supports."""
+        w = self._p(name + ".weight")
+        return ops.conv3x3_rmsnorm_cl(x, self._packed.get(name, w), self._p(name + ".bias"), cout, kt, gamma,
+                                      silu=True, want_raw=want_raw, residual=residual)
+
+    def _res(self, x: Tensor, name: str, cin: int, cout: int, x_normed: Optional[Tensor] = None,
+             next_gamma: Optional[Tensor] = None):
+        """ResidualBlock (vae:190-224).  `x_normed` = SiLU(RMS_norm(x)) if the producer of x already
+        emitted it; `next_gamma` asks this block to emit the same for its consumer.  Returns
+        (out, out_normed or None)."""
         h = x if cin == cout else self._conv(x, name + ".shortcut", (1, 1, 1), cout, (0, 0, 0))
-        y = ops.rmsnorm_silu_cl(x, self._p(name + ".residual.0.gamma"))
-        c1 = self._conv(y, name + ".residual.2", (3, 3, 3), cout, (2, 1, 1))
+        y = x_normed if x_normed is not None else ops.rmsnorm_silu_cl(x, self._p(name + ".residual.0.gamma"))
+        fuse = self.fuse_norms and cout in ops.FUSED_NORM_CHANNELS
+        if fuse:
+            _, c1 = self._conv_norm(y, name + ".residual.2", 3, cout, self._p(name + ".residual.3.gamma"),
+                                    want_raw=False)
+        else:
+            c1 = self._conv(y, name + ".residual.2", (3, 3, 3), cout, (2, 1, 1))
+            ops.rmsnorm_silu_cl(c1, self._p(name + ".residual.3.gamma"), inplace=True)
         del y
-        ops.rmsnorm_silu_cl(c1, self._p(name + ".residual.3.gamma"), inplace=True)
-        return self._conv(c1, name + ".residual.6", (3, 3, 3), cout, (2, 1, 1), residual=h)
+        if fuse and next_gamma is not None:
+            return self._conv_norm(c1, name + ".residual.6", 3, cout, next_gamma, residual=h)
+        return self._conv(c1, name + ".residual.6", (3, 3, 3), cout, (2, 1, 1), residual=h), None
 
     def _attn(self, x: Tensor, name: str) -> Tensor:
         T, H, W, C = x.shape
@@ -197,7 +217,7 @@ class AutoencoderKLWan(nn.Module):
             y = out
         return y
 
-    def _up(self, x: Tensor, name: str, kind: str, c: int) -> Tensor:
+    def _up(self, x: Tensor, name: str, kind: str, c: int, next_gamma: Optional[Tensor] = None):
         T, H, W, _ = x.shape
         if kind == "up3d" and T > 1:
             u = torch.empty(1 + 2 * (T - 1), H, W, c, device=x.device, dtype=BF16)
@@ -206,21 +226,36 @@ class AutoencoderKLWan(nn.Module):
                        t_mul=2, t_off=1, n_split=c)
             x = u
         up = ops.upsample2x_cl(x)
-        return self._conv(up, name + ".resample.1", (1, 3, 3), c // 2, (0, 1, 1))
+        if next_gamma is not None and self.fuse_norms and c // 2 in ops.FUSED_NORM_CHANNELS:
+            return self._conv_norm(up, name + ".resample.1", 1, c // 2, next_gamma)
+        return self._conv(up, name + ".resample.1", (1, 3, 3), c // 2, (0, 1, 1)), None
 
-    def _run(self, x: Tensor, layers) -> Tensor:
-        for kind, name, cin, cout in layers:
+    def _next_gamma(self, layers, i: int, tail_gamma: Optional[Tensor]) -> Optional[Tensor]:
+        """gamma of the RMS_norm that consumes layer i's output first, if that is how it is
+        consumed (a ResidualBlock's residual.0, or the head norm after the last layer)."""
+        if i + 1 < len(layers):
+            kind, name = layers[i + 1][0], layers[i + 1][1]
+            return self._p(name + ".residual.0.gamma") if kind == "res" else None
+        return tail_gamma
+
+    def _run(self, x: Tensor, layers, x_normed: Optional[Tensor] = None,
+             tail_gamma: Optional[Tensor] = None):
+        """Runs the layer program; returns (x, SiLU(RMS_norm(x) * tail_gamma) or None)."""
+        for i, (kind, name, cin, cout) in enumerate(layers):
+            ng = self._next_gamma(layers, i, tail_gamma)
+            xn = None
             if kind == "conv":
                 x = self._conv(x, name, (3, 3, 3), cout, (2, 1, 1))
             elif kind == "res":
-                x = self._res(x, name, cin, cout)
+                x, xn = self._res(x, name, cin, cout, x_normed, ng)
             elif kind == "attn":
                 x = self._attn(x, name)
             elif kind in ("down2d", "down3d"):
                 x = self._down(x, name, kind, cin)
             elif kind in ("up2d", "up3d"):
-                x = self._up(x, name, kind, cin)
-        return x
+                x, xn = self._up(x, name, kind, cin, ng)
+            x_normed = xn
+        return x, x_normed
 
     # --------------------------------------------------------------------------- encode / decode
     def _encode_one(self, x: Tensor, in_scale: float = 1.0, in_shift: float = 0.0) -> Tensor:
@@ -230,12 +265,20 @@ class AutoencoderKLWan(nn.Module):
         # 3-channel input: zero-padded to 32 channels so the first conv also runs on the tensor
         # cores (K = 27 x 32); the optional `x*2-1` is fused into the layout pass
         xc = self._input_cl(x, in_scale, in_shift)
-        h = self._conv(xc, "encoder.conv1", (3, 3, 3), layers[0][3], (2, 1, 1))
-        del xc
-        h = self._run(h, layers[1:-1])
+        body = layers[1:-1]
         _, hname, cin, cout = layers[-1]
-        ops.rmsnorm_silu_cl(h, self._p(hname + ".0.gamma"), inplace=True)
-        h = self._conv(h, hname + ".2", (3, 3, 3), cout, (2, 1, 1))
+        c0, hn = layers[0][3], None
+        g0 = self._next_gamma(body, -1, None)
+        if g0 is not None and self.fuse_norms and c0 in ops.FUSED_NORM_CHANNELS:
+            h, hn = self._conv_norm(xc, "encoder.conv1", 3, c0, g0)
+        else:
+            h = self._conv(xc, "encoder.conv1", (3, 3, 3), c0, (2, 1, 1))
+        del xc
+        h, hn = self._run(h, body, hn, self._p(hname + ".0.gamma"))
+        if hn is None:
+            hn = ops.rmsnorm_silu_cl(h, self._p(hname + ".0.gamma"), inplace=True)
+        del h
+        h = self._conv(hn, hname + ".2", (3, 3, 3), cout, (2, 1, 1))
         h = self._conv(h, "conv1", (1, 1, 1), cout, (0, 0, 0))
         mean, inv_std = self._affine_consts()
         return ops.cl_to_planar(h, cfg.z_dim, mean, inv_std)
@@ -249,9 +292,12 @@ class AutoencoderKLWan(nn.Module):
         T, h, w, _ = zc.shape
         z2 = torch.zeros(T, h, w, 32, device=z.device, dtype=BF16)       # channels 16..31 stay zero
         self._conv(zc, "conv2", (1, 1, 1), cfg.z_dim, (0, 0, 0), out=z2)
-        x = self._run(z2, layers[:-1])
         _, hname, cin, cout = layers[-1]
-        ops.rmsnorm_silu_cl(x, self._p(hname + ".0.gamma"), inplace=True)
+        x, xn = self._run(z2, layers[:-1], None, self._p(hname + ".0.gamma"))
+        if xn is None:
+            xn = ops.rmsnorm_silu_cl(x, self._p(hname + ".0.gamma"), inplace=True)
+        del x
+        x = xn
         To, H, W, _ = x.shape
         video = torch.empty(cout, To, H, W, device=z.device, dtype=BF16)
         self._conv(x, hname + ".2", (3, 3, 3), cout, (2, 1, 1), planar_out=video, act=1)

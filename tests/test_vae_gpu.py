@@ -73,6 +73,53 @@ def test_conv_residual_and_pointwise(ops):
     assert rel_err(_ncthw(y), ref) < 3e-3
 
 
+@pytest.mark.parametrize("cin,cout,T,H,W,kt,res", [
+    (96, 96, 3, 20, 37, 3, True),       # ragged tiles, residual, two 64-channel blocks (64 + 32)
+    (192, 192, 2, 16, 16, 3, False),    # exactly one tile, single accumulator set
+    (384, 192, 2, 9, 33, 1, False),     # upsample-branch Conv2d shape (kt = 1)
+    (32, 96, 2, 18, 18, 3, False),      # half-filled channel block (encoder.conv1)
+])
+def test_conv3x3_fused_rmsnorm(ops, cin, cout, T, H, W, kt, res):
+    """m4d_conv3x3_rmsnorm_cl == m4d_conv_cl followed by m4d_rmsnorm_silu_cl, and == the oracle."""
+    x = _rand((1, cin, T, H, W), 31)
+    w = _rand((cout, cin, kt, 3, 3), 32, (cin * 9 * kt) ** -0.5)
+    b = _rand((cout,), 33, 0.1)
+    g = _rand((cout, 1, 1, 1), 34, 0.1) + 1
+    r = _rand((1, cout, T, H, W), 35) if res else None
+    wp = ops.pack_conv_weight(w.cuda())
+    rg = _cl(r) if res else None
+    raw, normed = ops.conv3x3_rmsnorm_cl(_cl(x), wp, b.cuda(), cout, kt, g.cuda().reshape(-1), residual=rg)
+    sep = ops.conv_cl(_cl(x), wp, b.cuda(), cout, (kt, 3, 3), pad=(kt - 1, 1, 1), residual=rg)
+    assert torch.equal(raw, sep)                                   # same kernel, same arithmetic
+    sep_n = ops.rmsnorm_silu_cl(sep, g.cuda().reshape(-1))
+    assert rel_err(normed.float(), sep_n.float()) < 1e-3           # sum-of-squares order differs
+    none_raw, normed2 = ops.conv3x3_rmsnorm_cl(_cl(x), wp, b.cuda(), cout, kt, g.cuda().reshape(-1),
+                                               want_raw=False, residual=rg)
+    assert none_raw is None and torch.equal(normed2, normed)
+    if kt == 3:
+        y = V.causal_conv3d(x.float(), w, b, AR)
+    else:
+        y = V.conv2d_frames(x.float(), w[:, :, 0], b, AR, stride=1, pad=(1, 1, 1, 1))
+    if res:
+        y = AR.r(y + r.float())
+    ref = V.silu(V.rms_norm(y, g, AR), AR)
+    assert rel_err(_ncthw(normed), ref) < 4e-3
+
+
+def test_vae_fused_norms_match_unfused():
+    """The fused-epilogue path and the separate-kernel path of the VAE agree."""
+    x = synth._randn(SEED, "vae.x", (1, 3, 5, 32, 48), 0.5, "cpu", BF16)
+    z = synth._randn(SEED, "vae.z", (1, 16, 2, 4, 6), 1.0, "cpu", BF16)
+    m = _vae()
+    outs = {}
+    with torch.no_grad():
+        for fuse in (True, False):
+            m.fuse_norms = fuse
+            outs[fuse] = (m.encode(x.cuda())[0].parameters.float().cpu(), m.decode(z.cuda()).sample.float().cpu())
+    assert rel_err(outs[True][0], outs[False][0]) < 1e-2
+    assert rel_err(outs[True][1], outs[False][1]) < 1e-2
+
+
 def test_conv2d_stride2_downsample(ops):
     c, T, H, W = 96, 2, 12, 20
     x = _rand((1, c, T, H, W), 8)

@@ -191,8 +191,11 @@ def attn_sweep():
     Q, K, V = (torch.randn(B, L, N, 128, device="cuda", dtype=BF16) for _ in range(3))
     out = torch.empty_like(Q)
     fl = 4.0 * B * N * L * L * 128
-    for pp, var in [(0, 0), (0, 2), (0, 0), (0, 2), (0, 0), (0, 2)]:
-        _lib.lib().m4d_set_debug_flags(0x600 if pp == 64 else (0x200 | 0x100 | (pp << 4) | var))
+    variants = [(0, 0, 0), (0, 0, 4), (0, 0, 2), (0, 0, 6), (2, 0, 4), (0, 0, 0), (0, 0, 4)]
+    if len(sys.argv) > 2:
+        variants = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]]
+    for pp, var, pace in variants:
+        _lib.lib().m4d_set_debug_flags(0x200 | 0x100 | (pp << 4) | var | 0x1000000 | (pace << 20))
         o = ops.attention(q.cuda(), k.cuda(), v.cuda())
         e = rel(o.float().cpu(), ref)
         ops.attention(Q, K, V, out=out)
@@ -205,7 +208,7 @@ def attn_sweep():
             e_.record(); torch.cuda.synchronize()
             ts.append(s_.elapsed_time(e_))
         ms = min(ts)
-        print(f"PP={pp} VAR={var}: parity rel={e:.3e}  {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s (all: {[round(t,1) for t in ts]})", flush=True)
+        print(f"PP={pp} VAR={var} PACE={pace}: parity rel={e:.3e}  {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s (all: {[round(t,1) for t in ts]})", flush=True)
     _lib.lib().m4d_set_debug_flags(0)
 
 
