@@ -32,7 +32,7 @@ constexpr int CH_A_BYTES = CH_HW * CH_HW * 128;  // 41472: [18][18] pixels x 64 
 constexpr int CH_A_STRIDE = 41 * 1024;           // ring stride (1024-B aligned for SWIZZLE_128B)
 constexpr int CH_ROW_BYTES = CH_HW * 128;        // one window row = stride between 8-pixel groups
 constexpr int CH_THREADS = 384;
-constexpr int CH_MAX_A = 3, CH_MAX_B = 8;
+constexpr int CH_MAX_A = 3, CH_MAX_B = 9;
 constexpr int CH_SMEM_MAX = 227 * 1024;
 
 // SWIZZLE_128B K-major descriptors as {lo, hi}: lo = (address >> 4) | LBO(16 B) << 16, hi = SBO >> 4 |
@@ -113,6 +113,10 @@ __device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t
   }
 }
 
+// BST = weight-ring depth, 3 or 9: a divisor of the 9 spatial taps, so ring slot and mbarrier
+// parity of every tap are compile-time functions of the tap index and of one running block
+// counter — the MMA issuer does no ring arithmetic between taps (see the issuer's comment).
+template <int BST>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  ConvParams p) {
@@ -122,7 +126,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int b_bytes = p.NT * 128;
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.a_stages * CH_A_STRIDE;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + p.stages * b_bytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + BST * b_bytes);
   uint64_t* a_empty = a_full + CH_MAX_A;
   uint64_t* b_full = a_empty + CH_MAX_A;
   uint64_t* b_empty = b_full + CH_MAX_B;
@@ -185,34 +189,40 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp == 3) {
     // ------------------------------------------------------------ weight producer
     if (lane == 0) {
-      int sb = 0;
-      uint32_t pb = 0;
+      uint32_t blk = 0;                                // running (time tap, channel block) counter
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int n_blk = tile % p.n_tiles;
         for (int a = 0; a < p.kt; ++a)
-          for (int cb = 0; cb < cblocks; ++cb)
+          for (int cb = 0; cb < cblocks; ++cb, ++blk) {
+#pragma unroll
             for (int tap9 = 0; tap9 < 9; ++tap9) {
-              mbar_wait(&b_empty[sb], pb ^ 1);
+              constexpr int per = 9 / BST;             // uses of a ring slot per block (odd)
+              const int sb = tap9 % BST;
+              const uint32_t use = blk * per + tap9 / BST;
+              mbar_wait(&b_empty[sb], (use & 1) ^ 1);
               mbar_arrive_expect_tx(&b_full[sb], b_bytes);
               tma_load_2d(sB + sb * b_bytes, &tmW, &b_full[sb], (a * 9 + tap9) * p.Cin + cb * 64,
                           n_blk * p.NT);
-              if (++sb == p.stages) {
-                sb = 0;
-                pb ^= 1;
-              }
             }
+          }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     // The whole warp runs the loops converged (operands stay in uniform registers); one
     // elected lane issues.  Descriptors are {lo, hi} pairs whose hi word is constant and whose
-    // lo word only takes compile-time offsets per (tap, sub-tile, k-slice): the issue rate of
-    // this thread bounds the N = 96 layers (48 clk per MMA).
+    // lo word only takes compile-time offsets per (tap, sub-tile, k-slice).  This thread's
+    // serial latency per weight stage (mbarrier probe, ring arithmetic, R2UR moves, commit) is
+    // what bounded the kernel (profiles/conv_halo_r01.md: tensor pipe 56 % at N = 96, 75 % at
+    // N = 192 with ~250 clocks of bookkeeping per stage), hence: static ring slots / parities
+    // (BST), and the NEXT stage's barrier is probed before the current stage's MMAs are issued.
     const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
+    const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t b_step = static_cast<uint32_t>(b_bytes) >> 4;
+    const bool leader = elect_one();
+    int sa = 0;
+    uint32_t pa = 0, blk = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int acc = it % p.acc_bufs;
@@ -222,19 +232,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t d_tmem = tmem_base + acc * 2 * p.acc_stride;
       const uint32_t d_tmem1 = d_tmem + p.acc_stride;
       for (int a = 0; a < p.kt; ++a)
-        for (int cb = 0; cb < cblocks; ++cb) {
+        for (int cb = 0; cb < cblocks; ++cb, ++blk) {
           const int ch_left = p.Cin - cb * 64;
           const int kslices = ch_left >= 64 ? 4 : (ch_left >> 4);
+          constexpr int per = 9 / BST;
+          bool ready = mbar_try_wait(&b_full[0], (blk * per) & 1);
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = (((a_base + sa * CH_A_STRIDE) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
           for (int tap9 = 0; tap9 < 9; ++tap9) {
-            mbar_wait(&b_full[sb], pb);
+            const int sb = tap9 % BST;
+            if (!ready) mbar_wait(&b_full[sb], (blk * per + tap9 / BST) & 1);
             tc_fence_after();
-            const uint32_t b_lo = (((b_base + sb * b_bytes) >> 4) & 0x3FFF) | (1u << 16);
+            if (tap9 < 8) ready = mbar_try_wait(&b_full[(tap9 + 1) % BST], (blk * per + (tap9 + 1) / BST) & 1);
+            const uint32_t b_lo = b_lo0 + sb * b_step;
             const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3)) * 8;
             const uint32_t acc0 = (a | cb | tap9) == 0 ? 0u : 1u;
-            if (elect_one()) {
+            if (leader) {
               if (kslices == 4) {
                 issue_tap<4>(d_tmem, d_tmem1, a_tap, b_lo, idesc, acc0);
               } else if (kslices == 2) {
@@ -248,22 +262,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 }
               }
               umma_commit(&b_empty[sb]);
-            }
-            __syncwarp();
-            if (++sb == p.stages) {
-              sb = 0;
-              pb ^= 1;
+              if (tap9 == 8) umma_commit(&a_empty[sa]);
             }
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);
-          __syncwarp();
           if (++sa == p.a_stages) {
             sa = 0;
             pa ^= 1;
           }
         }
-      if (elect_one()) umma_commit(&tfull[acc]);
-      __syncwarp();
+      if (leader) umma_commit(&tfull[acc]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
@@ -337,14 +344,12 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   }
   const int b_bytes = NT * 128;
   const int fixed = 1024 + 512;                         // alignment slack + barriers
-  p.a_stages = 2;
-  int stages = (CH_SMEM_MAX - fixed - p.a_stages * CH_A_STRIDE) / b_bytes;
-  if ((CH_SMEM_MAX - fixed - 3 * CH_A_STRIDE) / b_bytes >= 6) {
-    p.a_stages = 3;
-    stages = (CH_SMEM_MAX - fixed - 3 * CH_A_STRIDE) / b_bytes;
-  }
-  p.stages = stages > CH_MAX_B ? CH_MAX_B : stages;
-  M4D_REQUIRE(p.stages >= 3, M4D_ERR_UNSUPPORTED);
+  // weight ring: all 9 taps of a block when that leaves room for >= 2 halo stages, else 3
+  const int bst = (CH_SMEM_MAX - fixed - 9 * b_bytes >= 2 * CH_A_STRIDE) ? 9 : 3;
+  p.stages = bst;
+  p.a_stages = (CH_SMEM_MAX - fixed - bst * b_bytes) / CH_A_STRIDE;
+  if (p.a_stages > CH_MAX_A) p.a_stages = CH_MAX_A;
+  M4D_REQUIRE(p.a_stages >= 2, M4D_ERR_UNSUPPORTED);
 
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return M4D_ERR_NO_DEVICE;
@@ -380,9 +385,11 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   const int smem_bytes = p.a_stages * CH_A_STRIDE + p.stages * b_bytes + fixed;
   static bool configured = false;
   if (!configured) {
-    int rc = cuda_ok(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          CH_SMEM_MAX),
-                     "cudaFuncSetAttribute(conv_halo)");
+    int rc = cuda_ok(cudaFuncSetAttribute(conv_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          CH_SMEM_MAX), "cudaFuncSetAttribute(conv_halo<3>)");
+    if (rc != M4D_OK) return rc;
+    rc = cuda_ok(cudaFuncSetAttribute(conv_halo_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      CH_SMEM_MAX), "cudaFuncSetAttribute(conv_halo<9>)");
     if (rc != M4D_OK) return rc;
     configured = true;
   }
@@ -390,7 +397,8 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
                           ((p.W_out + CH_T - 1) / CH_T) * p.n_tiles;
   M4D_REQUIRE(tiles < (1ll << 31), M4D_ERR_BAD_SHAPE);
   const int grid = tiles < sm_count() ? static_cast<int>(tiles) : sm_count();
-  conv_halo_kernel<<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
+  if (bst == 9) conv_halo_kernel<9><<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
+  else conv_halo_kernel<3><<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
   M4D_CHECK_LAUNCH("conv_halo_kernel");
   return M4D_OK;
 }
