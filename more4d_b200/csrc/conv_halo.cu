@@ -113,6 +113,30 @@ __device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t
   }
 }
 
+// The nine spatial taps of one (time tap, 64-channel block): wait for each weight stage, issue,
+// release it.  Ring slot and parity are compile-time functions of the tap; the next stage's
+// barrier is probed before the current stage's MMAs are issued so its latency is hidden.
+template <int BST, int KS>
+__device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, uint64_t* a_empty_bar,
+                                          uint32_t blk, uint32_t a_lo, uint32_t b_lo0, uint32_t b_step,
+                                          uint32_t d0, uint32_t d1, uint32_t idesc, bool first_block,
+                                          bool ready) {
+  constexpr int per = 9 / BST;
+#pragma unroll
+  for (int tap9 = 0; tap9 < 9; ++tap9) {
+    const int sb = tap9 % BST;
+    if (!ready) mbar_wait(&b_full[sb], (blk * per + tap9 / BST) & 1);
+    tc_fence_after();
+    if (tap9 < 8) ready = mbar_try_wait(&b_full[(tap9 + 1) % BST], (blk * per + (tap9 + 1) / BST) & 1);
+    const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3)) * 8;
+    if (elect_one()) {
+      issue_tap<KS>(d0, d1, a_tap, b_lo0 + sb * b_step, idesc, (first_block && tap9 == 0) ? 0u : 1u);
+      umma_commit(&b_empty[sb]);
+      if (tap9 == 8) umma_commit(a_empty_bar);
+    }
+  }
+}
+
 // BST = weight-ring depth, 3 or 9: a divisor of the 9 spatial taps, so ring slot and mbarrier
 // parity of every tap are compile-time functions of the tap index and of one running block
 // counter — the MMA issuer does no ring arithmetic between taps (see the issuer's comment).
@@ -220,7 +244,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
     const uint32_t b_step = static_cast<uint32_t>(b_bytes) >> 4;
-    const bool leader = elect_one();
     int sa = 0;
     uint32_t pa = 0, blk = 0;
     int it = 0;
@@ -236,41 +259,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int ch_left = p.Cin - cb * 64;
           const int kslices = ch_left >= 64 ? 4 : (ch_left >> 4);
           constexpr int per = 9 / BST;
-          bool ready = mbar_try_wait(&b_full[0], (blk * per) & 1);
+          const bool ready = mbar_try_wait(&b_full[0], (blk * per) & 1);
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = (((a_base + sa * CH_A_STRIDE) >> 4) & 0x3FFF) | (1u << 16);
-#pragma unroll
-          for (int tap9 = 0; tap9 < 9; ++tap9) {
-            const int sb = tap9 % BST;
-            if (!ready) mbar_wait(&b_full[sb], (blk * per + tap9 / BST) & 1);
-            tc_fence_after();
-            if (tap9 < 8) ready = mbar_try_wait(&b_full[(tap9 + 1) % BST], (blk * per + (tap9 + 1) / BST) & 1);
-            const uint32_t b_lo = b_lo0 + sb * b_step;
-            const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3)) * 8;
-            const uint32_t acc0 = (a | cb | tap9) == 0 ? 0u : 1u;
-            if (leader) {
-              if (kslices == 4) {
-                issue_tap<4>(d_tmem, d_tmem1, a_tap, b_lo, idesc, acc0);
-              } else if (kslices == 2) {
-                issue_tap<2>(d_tmem, d_tmem1, a_tap, b_lo, idesc, acc0);
-              } else {
-                for (int k = 0; k < kslices; ++k) {
-                  umma_ss(d_tmem, desc_pair(a_tap + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B),
-                          idesc, acc0 | (k != 0));
-                  umma_ss(d_tmem1, desc_pair(a_tap + 64 + 2 * k, CH_DESC_HI_A),
-                          desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc, acc0 | (k != 0));
-                }
-              }
-              umma_commit(&b_empty[sb]);
-              if (tap9 == 8) umma_commit(&a_empty[sa]);
-            }
+          const bool first = (a | cb) == 0;
+          switch (kslices) {
+            case 4: mma_block<BST, 4>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+            case 2: mma_block<BST, 2>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+            case 3: mma_block<BST, 3>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+            default: mma_block<BST, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
           }
           if (++sa == p.a_stages) {
             sa = 0;
             pa ^= 1;
           }
         }
-      if (leader) umma_commit(&tfull[acc]);
+      if (elect_one()) umma_commit(&tfull[acc]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
