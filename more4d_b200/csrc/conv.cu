@@ -43,7 +43,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr) {
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_cl_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-               ConvParams p) {
+               const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -255,7 +255,7 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(x && w_packed && (out || norm_out), M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(T_in > 0 && H_in > 0 && W_in > 0 && T_out > 0 && H_out > 0 && W_out > 0, M4D_ERR_BAD_SHAPE);
-  M4D_REQUIRE(Cin > 0 && Cin % CV_KB == 0, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(Cin > 0 && Cin % 16 == 0, M4D_ERR_UNSUPPORTED);
   M4D_REQUIRE(Cout > 0 && Cout_pad >= Cout && Cout_pad % 16 == 0, M4D_ERR_UNSUPPORTED);
   M4D_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && st >= 1 && sh >= 1 && sw >= 1 && sh <= 2 && sw <= 2,
               M4D_ERR_UNSUPPORTED);
@@ -291,6 +291,9 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
   p.norm_gamma = static_cast<const bf16*>(norm_gamma);
   p.norm_out = static_cast<bf16*>(norm_out);
   p.norm_silu = norm_silu;
+  p.vec_ok = (out_mode == 0 && out_C % 8 == 0 && n_split % 8 == 0 && (out == nullptr || aligned16(out)) &&
+              (bias == nullptr || aligned16(bias)) && (residual == nullptr || aligned16(residual)))
+                 ? 1 : 0;
 
   // 3x3 (x kt) stride-1 convolutions — almost all of the VAE's FLOPs — take the halo-staging
   // kernel (conv_halo.cu); debug flag 0x10000 forces the per-tap kernel below.
@@ -298,6 +301,7 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
       conv_halo_eligible(Cin, kt, kh, kw, st, sh, sw, pt, ph, pw, T_in, H_in, W_in, T_out, H_out, W_out))
     return conv_halo_launch(x, T_in, H_in, W_in, w_packed, Cout_pad, p, stream);
   M4D_REQUIRE(norm_out == nullptr, M4D_ERR_UNSUPPORTED);      // the fused norm lives in conv_halo.cu
+  M4D_REQUIRE(Cin % CV_KB == 0, M4D_ERR_UNSUPPORTED);         // per-tap kernel: 32-channel boxes
 
   CUtensorMap tmX, tmW;
   {

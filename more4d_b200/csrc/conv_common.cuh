@@ -36,42 +36,51 @@ struct ConvParams {
   const bf16* norm_gamma;
   bf16* norm_out;
   int norm_silu;
+  int vec_ok;               // NHWC rows, bias and residual allow 16-byte vector access per 32 channels
 };
 
 // SiLU on a bf16-rounded input, result rounded to bf16 (reference: nn.SiLU on a bf16 tensor).
 // __fdividef / __expf: the <= 2 ulp fp32 error is invisible after the bf16 rounding.
 __device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(__fdividef(x, 1.f + __expf(-x))); }
 
-// Final bf16 values (as floats) of output pixel (t, h, w), channels [n0, n0 + 32), NHWC mode with
-// all 32 channels valid: bias, bf16 rounding (the reference's bf16 conv output), residual add
-// (ResidualBlock, vae:224) and its rounding.  Returns the element offset of the chunk.
-__device__ __forceinline__ long long conv_chunk_values(const ConvParams& p, const uint32_t* rr, int t,
-                                                       int h, int w, int n0, float* v, bool pix_ok) {
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
+
+// Final bf16 values (as floats) of 32 consecutive, fully valid output channels of one pixel:
+// bias (16-byte aligned vector loads), bf16 rounding (the reference's bf16 conv output), then
+// the residual add (ResidualBlock, vae:224) and its rounding.  `bias`, `res` point at the
+// chunk's first channel or are null.
+__device__ __forceinline__ void conv_chunk_values(const uint32_t* rr, const bf16* bias, const bf16* res,
+                                                  float* v) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = __uint_as_float(rr[i]);
-    if (p.bias != nullptr) v[i] += __bfloat162float(p.bias[n0 + i]);
-    v[i] = bf16_round(v[i]);
-  }
-  const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
-  const int ch = n0 % p.n_split;
-  const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
-  if (p.residual != nullptr && pix_ok) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-    uint4 u4[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) u4[q] = rp[q];
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+  if (bias != nullptr) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint32_t ww[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
+      float b8[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(bias) + q), b8);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[q * 8 + 2 * e] = bf16_round(v[q * 8 + 2 * e] + __uint_as_float(ww[e] << 16));
-        v[q * 8 + 2 * e + 1] = bf16_round(v[q * 8 + 2 * e + 1] + __uint_as_float(ww[e] & 0xFFFF0000u));
-      }
+      for (int e = 0; e < 8; ++e) v[q * 8 + e] += b8[e];
     }
   }
-  return off;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+  if (res != nullptr) {
+    uint4 u4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u4[q] = reinterpret_cast<const uint4*>(res)[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float r8[8];
+      unpack8(u4[q], r8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[q * 8 + e] = bf16_round(v[q * 8 + e] + r8[e]);
+    }
+  }
 }
 
 __device__ __forceinline__ void store_chunk_bf16(bf16* o, const float* v) {
@@ -86,60 +95,31 @@ __device__ __forceinline__ void store_chunk_bf16(bf16* o, const float* v) {
   }
 }
 
-// Epilogue of output pixel (t, h, w), channels [n0, n0 + 32): rr = fp32 accumulators.
-// bias, bf16 rounding (the reference's bf16 conv output), residual add, store.
-__device__ __forceinline__ void conv_store_chunk(const ConvParams& p, const uint32_t* rr, int t, int h,
-                                                 int w, int n0) {
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = __uint_as_float(rr[i]);
-    if (p.bias != nullptr && n0 + i < p.Cout) v[i] += __bfloat162float(p.bias[n0 + i]);
-    v[i] = bf16_round(v[i]);
-  }
+// Ragged / planar tail of the epilogue (channel counts that are not multiples of 32, unaligned
+// rows, the 3-channel planar outputs with clamp / sigmoid): element-wise, kept out of line so
+// its dynamically indexed accumulators do not drag the common path into local memory.
+static __device__ __noinline__ void conv_store_chunk_slow(const ConvParams& p, const uint32_t* rr, int t, int h,
+                                                   int w, int n0) {
+  const int nvalid = min(32, p.Cout - n0);
   if (p.out_mode == 0) {
     const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
     const int ch = n0 % p.n_split;
     const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
     bf16* o = reinterpret_cast<bf16*>(p.out) + off;
-    const int nvalid = min(32, p.Cout - n0);
-    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-      if (p.residual != nullptr) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-        uint4 u4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) u4[q] = rp[q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t ww[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[q * 8 + 2 * e] += __uint_as_float(ww[e] << 16);
-            v[q * 8 + 2 * e + 1] += __uint_as_float(ww[e] & 0xFFFF0000u);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-        u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-        u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-        reinterpret_cast<uint4*>(o)[q] = u;
-      }
-    } else {
-      for (int i = 0; i < nvalid; ++i) {
-        float y = v[i];
-        if (p.residual != nullptr) y += __bfloat162float(p.residual[off + i]);
-        o[i] = __float2bfloat16_rn(y);
-      }
+    for (int i = 0; i < nvalid; ++i) {
+      float y = __uint_as_float(rr[i]);
+      if (p.bias != nullptr) y += __bfloat162float(p.bias[n0 + i]);
+      y = bf16_round(y);
+      if (p.residual != nullptr) y += __bfloat162float(p.residual[off + i]);
+      o[i] = __float2bfloat16_rn(y);
     }
   } else {
     // planar NCTHW output of a few channels (decoder head / adaptor conv_out)
     const long long pix = (static_cast<long long>(t) * p.H_out + h) * p.W_out + w;
-    for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
-      float y = v[i];
+    for (int i = 0; i < nvalid; ++i) {
+      float y = __uint_as_float(rr[i]);
+      if (p.bias != nullptr) y += __bfloat162float(p.bias[n0 + i]);
+      y = bf16_round(y);
       const long long off = (n0 + i) * p.planar_cstride + pix;
       if (p.act == 1) y = fminf(1.f, fmaxf(-1.f, y));
       if (p.act == 2) {
@@ -148,6 +128,22 @@ __device__ __forceinline__ void conv_store_chunk(const ConvParams& p, const uint
       }
       reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(y);
     }
+  }
+}
+
+// Epilogue of output pixel (t, h, w), channels [n0, n0 + 32): rr = fp32 accumulators.
+// bias, bf16 rounding (the reference's bf16 conv output), residual add, store.
+__device__ __forceinline__ void conv_store_chunk(const ConvParams& p, const uint32_t* rr, int t, int h,
+                                                 int w, int n0) {
+  if (p.out_mode == 0 && n0 + 32 <= p.Cout && p.vec_ok) {
+    const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
+    const int ch = n0 % p.n_split;
+    const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
+    float v[32];
+    conv_chunk_values(rr, p.bias ? p.bias + n0 : nullptr, p.residual ? p.residual + off : nullptr, v);
+    store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + off, v);
+  } else {
+    conv_store_chunk_slow(p, rr, t, h, w, n0);
   }
 }
 

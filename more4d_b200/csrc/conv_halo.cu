@@ -67,19 +67,19 @@ __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_l
 // (when p.out != null) and the normalised one; removes one read + one write of the activation
 // and a kernel launch per RMS_norm.
 template <int NTC>
-__device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t_row, int t, int h, int w,
+__device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t_row, long long pix_off,
                                                  bool pix_ok) {
   uint32_t yp[NTC / 2];
   float ss = 0.f;
-  long long off0 = 0;
 #pragma unroll
   for (int c0 = 0; c0 < NTC; c0 += 32) {
     uint32_t rr[32];
     tmem_ld32(t_row + c0, rr);
     tmem_ld_wait();
     float v[32];
-    const long long off = conv_chunk_values(p, rr, t, h, w, c0, v, pix_ok);
-    if (c0 == 0) off0 = off;
+    const long long off = pix_off + c0;
+    conv_chunk_values(rr, p.bias ? p.bias + c0 : nullptr,
+                      (p.residual != nullptr && pix_ok) ? p.residual + off : nullptr, v);
     if (p.out != nullptr && pix_ok) store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + off, v);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t
   if (!pix_ok) return;
   const float inv = 1.0f / fmaxf(bf16_round(sqrtf(ss)), 1e-12f);
   const float sc = sqrtf(static_cast<float>(NTC));
-  bf16* o = p.norm_out + off0;
+  bf16* o = p.norm_out + pix_off;
 #pragma unroll
   for (int c0 = 0; c0 < NTC; c0 += 8) {
     const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.norm_gamma + c0));
@@ -116,23 +116,40 @@ __device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t
 // The nine spatial taps of one (time tap, 64-channel block): wait for each weight stage, issue,
 // release it.  Ring slot and parity are compile-time functions of the tap; the next stage's
 // barrier is probed before the current stage's MMAs are issued so its latency is hidden.
-template <int BST, int KS>
+template <int BST, int KS, int TPB>
 __device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, uint64_t* a_empty_bar,
                                           uint32_t blk, uint32_t a_lo, uint32_t b_lo0, uint32_t b_step,
                                           uint32_t d0, uint32_t d1, uint32_t idesc, bool first_block,
                                           bool ready) {
-  constexpr int per = 9 / BST;
+  constexpr int G = (9 + TPB - 1) / TPB;
+  constexpr int per = G / BST;
 #pragma unroll
-  for (int tap9 = 0; tap9 < 9; ++tap9) {
-    const int sb = tap9 % BST;
-    if (!ready) mbar_wait(&b_full[sb], (blk * per + tap9 / BST) & 1);
+  for (int g = 0; g < G; ++g) {
+    const int sb = g % BST;
+    if (!ready) mbar_wait(&b_full[sb], (blk * per + g / BST) & 1);
     tc_fence_after();
-    if (tap9 < 8) ready = mbar_try_wait(&b_full[(tap9 + 1) % BST], (blk * per + (tap9 + 1) / BST) & 1);
-    const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3)) * 8;
+    if (g + 1 < G) ready = mbar_try_wait(&b_full[(g + 1) % BST], (blk * per + (g + 1) / BST) & 1);
+    const uint32_t b_lo = b_lo0 + sb * b_step;
     if (elect_one()) {
-      issue_tap<KS>(d0, d1, a_tap, b_lo0 + sb * b_step, idesc, (first_block && tap9 == 0) ? 0u : 1u);
+      if (TPB == 1) {
+        const uint32_t a_tap = a_lo + ((g / 3) * CH_HW + (g % 3)) * 8;
+        issue_tap<KS>(d0, d1, a_tap, b_lo, idesc, (first_block && g == 0) ? 0u : 1u);
+      } else {
+        // thin input: the box holds TPB taps x KS k-slices; slice q -> tap g*TPB + q/KS
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int tap9 = g * TPB + q / KS;
+            if (tap9 < 9) {
+              const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3) + 8 * sub) * 8 + 2 * (q % KS);
+              umma_ss(sub ? d1 : d0, desc_pair(a_tap, CH_DESC_HI_A), desc_pair(b_lo + 2 * q, CH_DESC_HI_B),
+                      idesc, (first_block && g == 0 && q == 0) ? 0u : 1u);
+            }
+          }
+      }
       umma_commit(&b_empty[sb]);
-      if (tap9 == 8) umma_commit(a_empty_bar);
+      if (g == G - 1) umma_commit(a_empty_bar);
     }
   }
 }
@@ -140,10 +157,15 @@ __device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, u
 // BST = weight-ring depth, 3 or 9: a divisor of the 9 spatial taps, so ring slot and mbarrier
 // parity of every tap are compile-time functions of the tap index and of one running block
 // counter — the MMA issuer does no ring arithmetic between taps (see the issuer's comment).
-template <int BST>
+//
+// TPB > 1 is the thin-input mode (Cin = 64 / TPB in {32, 16}: the zero-padded 3-channel model
+// inputs and the 16-channel latent): K is tap-major / channel-minor, so ONE 64-wide weight box
+// covers TPB consecutive taps and a block of nine taps needs G = ceil(9 / TPB) weight stages
+// (BST = G) instead of nine half-empty ones; k-slice q of a box belongs to tap g*TPB + q/KS.
+template <int BST, int TPB>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                 ConvParams p) {
+                 const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -218,14 +240,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int n_blk = tile % p.n_tiles;
         for (int a = 0; a < p.kt; ++a)
           for (int cb = 0; cb < cblocks; ++cb, ++blk) {
+            constexpr int G = (9 + TPB - 1) / TPB;     // weight stages per block
 #pragma unroll
-            for (int tap9 = 0; tap9 < 9; ++tap9) {
-              constexpr int per = 9 / BST;             // uses of a ring slot per block (odd)
-              const int sb = tap9 % BST;
-              const uint32_t use = blk * per + tap9 / BST;
+            for (int g = 0; g < G; ++g) {
+              constexpr int per = G / BST;             // uses of a ring slot per block (odd)
+              const int sb = g % BST;
+              const uint32_t use = blk * per + g / BST;
               mbar_wait(&b_empty[sb], (use & 1) ^ 1);
               mbar_arrive_expect_tx(&b_full[sb], b_bytes);
-              tma_load_2d(sB + sb * b_bytes, &tmW, &b_full[sb], (a * 9 + tap9) * p.Cin + cb * 64,
+              tma_load_2d(sB + sb * b_bytes, &tmW, &b_full[sb], (a * 9 + g * TPB) * p.Cin + cb * 64,
                           n_blk * p.NT);
             }
           }
@@ -258,16 +281,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int cb = 0; cb < cblocks; ++cb, ++blk) {
           const int ch_left = p.Cin - cb * 64;
           const int kslices = ch_left >= 64 ? 4 : (ch_left >> 4);
-          constexpr int per = 9 / BST;
+          constexpr int per = ((9 + TPB - 1) / TPB) / BST;
           const bool ready = mbar_try_wait(&b_full[0], (blk * per) & 1);
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = (((a_base + sa * CH_A_STRIDE) >> 4) & 0x3FFF) | (1u << 16);
           const bool first = (a | cb) == 0;
-          switch (kslices) {
-            case 4: mma_block<BST, 4>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
-            case 2: mma_block<BST, 2>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
-            case 3: mma_block<BST, 3>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
-            default: mma_block<BST, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+          if (TPB > 1) {
+            mma_block<BST, 4 / TPB, TPB>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready);
+          } else {
+            switch (kslices) {
+              case 4: mma_block<BST, 4, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+              case 2: mma_block<BST, 2, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+              case 3: mma_block<BST, 3, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+              default: mma_block<BST, 1, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+            }
           }
           if (++sa == p.a_stages) {
             sa = 0;
@@ -293,13 +320,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const bool pix_ok = (h < p.H_out) && (w < p.W_out);
       const int acc = it % p.acc_bufs;
       const uint32_t acc_phase = (it / p.acc_bufs) & 1;
+      // halo convs never interleave channels into frames (n_split >= Cout, checked on the host):
+      // one 64-bit offset per pixel, no per-chunk divisions
+      const long long pix_off = ((static_cast<long long>(t * p.t_mul + p.t_off) * p.H_out + h) * p.W_out + w) *
+                                    p.out_C + n_blk * p.NT;
+      if (p.residual != nullptr && pix_ok && p.out_mode == 0) {
+        // pull this pixel's residual row towards L2 while the tile's MMAs are still running:
+        // the epilogue's residual loads otherwise pay full HBM latency per 32-channel chunk
+        const char* rp = reinterpret_cast<const char*>(p.residual + pix_off);
+        for (int bo = 0; bo < p.NT * 2; bo += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + bo));
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              acc * 2 * p.acc_stride + sub * p.acc_stride;
       if (p.norm_out != nullptr) {                     // NT == Cout in {96, 192}, checked on the host
-        if (p.NT == 96) epilogue_rmsnorm<96>(p, t_row, t, h, w, pix_ok);
-        else epilogue_rmsnorm<192>(p, t_row, t, h, w, pix_ok);
+        if (p.NT == 96) epilogue_rmsnorm<96>(p, t_row, pix_off, pix_ok);
+        else epilogue_rmsnorm<192>(p, t_row, pix_off, pix_ok);
       } else {
         for (int c0 = 0; c0 < p.NT; c0 += 32) {
           const int n0 = n_blk * p.NT + c0;
@@ -308,7 +346,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld32(t_row + c0, rr);
           tmem_ld_wait();
           if (!pix_ok) continue;
-          conv_store_chunk(p, rr, t, h, w, n0);
+          if (p.vec_ok && n0 + 32 <= p.Cout) {
+            float v[32];
+            conv_chunk_values(rr, p.bias ? p.bias + n0 : nullptr,
+                              p.residual ? p.residual + pix_off + c0 : nullptr, v);
+            store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + pix_off + c0, v);
+          } else {
+            conv_store_chunk_slow(p, rr, t, h, w, n0);
+          }
         }
       }
       tc_fence_before();
@@ -325,7 +370,7 @@ bool conv_halo_eligible(int Cin, int kt, int kh, int kw, int st, int sh, int sw,
                         int T_in, int H_in, int W_in, int T_out, int H_out, int W_out) {
   (void)T_in; (void)T_out; (void)pt;
   return kh == 3 && kw == 3 && (kt == 1 || kt == 3) && st == 1 && sh == 1 && sw == 1 && ph == 1 &&
-         pw == 1 && Cin % 32 == 0 && H_out == H_in && W_out == W_in;
+         pw == 1 && Cin % 16 == 0 && H_out == H_in && W_out == W_in;
 }
 
 int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_packed, int Cout_pad,
@@ -338,7 +383,9 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   p.acc_stride = (NT + 31) & ~31;
   p.acc_bufs = (4 * p.acc_stride <= 512) ? 2 : 1;
   p.desc_mode = 0;
+  M4D_REQUIRE(p.out_mode == 1 || p.n_split >= p.Cout, M4D_ERR_UNSUPPORTED);
   if (p.norm_out != nullptr) {
+    M4D_REQUIRE(p.vec_ok, M4D_ERR_ALIGN);
     M4D_REQUIRE(p.norm_gamma != nullptr && p.out_mode == 0 && p.n_tiles == 1 && NT == p.Cout &&
                     (NT == 96 || NT == 192) && p.n_split >= p.Cout && p.out_C % 8 == 0,
                 M4D_ERR_UNSUPPORTED);
@@ -348,8 +395,12 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   }
   const int b_bytes = NT * 128;
   const int fixed = 1024 + 512;                         // alignment slack + barriers
-  // weight ring: all 9 taps of a block when that leaves room for >= 2 halo stages, else 3
-  const int bst = (CH_SMEM_MAX - fixed - 9 * b_bytes >= 2 * CH_A_STRIDE) ? 9 : 3;
+  // thin-input mode: Cin in {16, 32} -> 4 / 2 taps per weight box, ring = stages per block
+  const int tpb = (p.Cin == 16) ? 4 : (p.Cin == 32 ? 2 : 1);
+  // weight ring: all stages of a block when that leaves room for >= 2 halo stages, else 3
+  int bst = (CH_SMEM_MAX - fixed - 9 * b_bytes >= 2 * CH_A_STRIDE) ? 9 : 3;
+  if (tpb == 2) bst = 5;
+  if (tpb == 4) bst = 3;
   p.stages = bst;
   p.a_stages = (CH_SMEM_MAX - fixed - bst * b_bytes) / CH_A_STRIDE;
   if (p.a_stages > CH_MAX_A) p.a_stages = CH_MAX_A;
@@ -387,22 +438,19 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
     }
   }
   const int smem_bytes = p.a_stages * CH_A_STRIDE + p.stages * b_bytes + fixed;
-  static bool configured = false;
-  if (!configured) {
-    int rc = cuda_ok(cudaFuncSetAttribute(conv_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          CH_SMEM_MAX), "cudaFuncSetAttribute(conv_halo<3>)");
+  void (*kern)(CUtensorMap, CUtensorMap, ConvParams) =
+      tpb == 4 ? conv_halo_kernel<3, 4> : tpb == 2 ? conv_halo_kernel<5, 2>
+      : bst == 9 ? conv_halo_kernel<9, 1> : conv_halo_kernel<3, 1>;
+  {
+    int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX),
+                     "cudaFuncSetAttribute(conv_halo)");
     if (rc != M4D_OK) return rc;
-    rc = cuda_ok(cudaFuncSetAttribute(conv_halo_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      CH_SMEM_MAX), "cudaFuncSetAttribute(conv_halo<9>)");
-    if (rc != M4D_OK) return rc;
-    configured = true;
   }
   const long long tiles = static_cast<long long>(p.T_out) * ((p.H_out + CH_T - 1) / CH_T) *
                           ((p.W_out + CH_T - 1) / CH_T) * p.n_tiles;
   M4D_REQUIRE(tiles < (1ll << 31), M4D_ERR_BAD_SHAPE);
   const int grid = tiles < sm_count() ? static_cast<int>(tiles) : sm_count();
-  if (bst == 9) conv_halo_kernel<9><<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
-  else conv_halo_kernel<3><<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
+  kern<<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
   M4D_CHECK_LAUNCH("conv_halo_kernel");
   return M4D_OK;
 }

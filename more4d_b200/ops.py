@@ -299,14 +299,15 @@ def silu_bf16(x: Tensor) -> Tensor:
 # ======================================================================================
 # Motion-Sensitive VAE ops (channels-last bf16 activations [T, H, W, C])
 # ======================================================================================
-def pack_conv_weight(w: Tensor) -> Tensor:
+def pack_conv_weight(w: Tensor, cin_multiple: int = 32) -> Tensor:
     """Reference conv weight [Cout, Cin, (kt,) kh, kw] -> implicit-GEMM operand
-    [Cout_pad16, taps * Cin_pad32] (tap-major, channel-minor, zero padded).  One-time weight
-    preprocessing, not on the per-call path."""
+    [Cout_pad16, taps * Cin_pad] (tap-major, channel-minor, zero padded; Cin padded to
+    `cin_multiple`: 32, or 16 for the thin 3-channel inputs of the 3x3 halo kernel).  One-time
+    weight preprocessing, not on the per-call path."""
     if w.dim() == 4:
         w = w.unsqueeze(2)
     cout, cin, kt, kh, kw = w.shape
-    cin_p, cout_p = (cin + 31) // 32 * 32, (cout + 15) // 16 * 16
+    cin_p, cout_p = (cin + cin_multiple - 1) // cin_multiple * cin_multiple, (cout + 15) // 16 * 16
     p = torch.zeros(cout_p, kt, kh, kw, cin_p, device=w.device, dtype=BF16)
     p[:cout, :, :, :, :cin] = w.permute(0, 2, 3, 4, 1).to(BF16)
     return p.reshape(cout_p, kt * kh * kw * cin_p).contiguous()
@@ -317,7 +318,8 @@ def conv_cl(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kern
             t_mul: int = 1, t_off: int = 0, n_split: Optional[int] = None,
             residual: Optional[Tensor] = None, planar_out: Optional[Tensor] = None, act: int = 0,
             skip: Optional[Tensor] = None) -> Tensor:
-    """Implicit-GEMM convolution over a channels-last sequence x [T, H, W, Cin] (Cin % 32 == 0).
+    """Implicit-GEMM convolution over a channels-last sequence x [T, H, W, Cin] (Cin % 32 == 0;
+    Cin % 16 == 0 for 3x3 stride-1 convolutions).
     `pad` = (front frames, top/left rows, cols); right/bottom/behind padding is implied by the
     output size.  Returns the channels-last output (or `planar_out` [Cout, T, H, W])."""
     _lib.require_device()

@@ -58,11 +58,11 @@ class _PackedWeights:
     def __init__(self):
         self._cache: Dict[str, tuple] = {}
 
-    def get(self, key: str, w: Tensor) -> Tensor:
-        tag = (w.data_ptr(), w._version, tuple(w.shape))
+    def get(self, key: str, w: Tensor, cin_multiple: int = 32) -> Tensor:
+        tag = (w.data_ptr(), w._version, tuple(w.shape), cin_multiple)
         hit = self._cache.get(key)
         if hit is None or hit[0] != tag:
-            hit = (tag, ops.pack_conv_weight(w.detach()))
+            hit = (tag, ops.pack_conv_weight(w.detach(), cin_multiple))
             self._cache[key] = hit
         return hit[1]
 
@@ -151,22 +151,24 @@ class AutoencoderKLWan(nn.Module):
 
     def _input_cl(self, x: Tensor, in_scale: float, in_shift: float) -> Tensor:
         if in_scale == 1.0 and in_shift == 0.0:
-            return ops.planar_to_cl(x, 32)
+            return ops.planar_to_cl(x, 16)
         dev = x.device
         div = torch.full((3,), 1.0 / in_scale, device=dev, dtype=torch.float32)
         add = torch.full((3,), in_shift, device=dev, dtype=torch.float32)
-        return ops.planar_to_cl(x, 32, div, add)
+        return ops.planar_to_cl(x, 16, div, add)
 
     def _conv(self, x: Tensor, name: str, kernel, cout: int, pad, **kw) -> Tensor:
         w = self._p(name + ".weight")
-        return ops.conv_cl(x, self._packed.get(name, w), self._p(name + ".bias"), cout, kernel, pad=pad, **kw)
+        mult = 16 if x.shape[-1] % 32 else 32               # thin (3 -> 16 channel) inputs
+        return ops.conv_cl(x, self._packed.get(name, w, mult), self._p(name + ".bias"), cout, kernel, pad=pad, **kw)
 
     def _conv_norm(self, x: Tensor, name: str, kt: int, cout: int, gamma: Tensor, want_raw: bool = True,
                    residual: Optional[Tensor] = None):
         """3x3 conv whose epilogue also emits [SiLU](RMS_norm(out) * gamma) — the consumer's first
         op (vae:198-202) — for the channel counts the fused epilogue supports."""
         w = self._p(name + ".weight")
-        return ops.conv3x3_rmsnorm_cl(x, self._packed.get(name, w), self._p(name + ".bias"), cout, kt, gamma,
+        mult = 16 if x.shape[-1] % 32 else 32
+        return ops.conv3x3_rmsnorm_cl(x, self._packed.get(name, w, mult), self._p(name + ".bias"), cout, kt, gamma,
                                       silu=True, want_raw=want_raw, residual=residual)
 
     def _res(self, x: Tensor, name: str, cin: int, cout: int, x_normed: Optional[Tensor] = None,
@@ -345,7 +347,8 @@ class _Adaptor(nn.Module):
 
     def _conv(self, x, name, cout, **kw):
         w = self._p(name + ".weight")
-        return ops.conv_cl(x, self._packed.get(name, w), self._p(name + ".bias"), cout, (1, 3, 3),
+        mult = 16 if x.shape[-1] % 32 else 32
+        return ops.conv_cl(x, self._packed.get(name, w, mult), self._p(name + ".bias"), cout, (1, 3, 3),
                            pad=(0, 1, 1), **kw)
 
     def _resnet(self, x: Tensor, p: str) -> Tensor:
@@ -371,7 +374,7 @@ class VAEEncoderadaptor(_Adaptor):
     kind = "encoder"
 
     def _forward_one(self, x: Tensor) -> Tensor:          # x [3, F, H, W]
-        h = self._conv(ops.planar_to_cl(x, 32), "conv_in", self.ch)
+        h = self._conv(ops.planar_to_cl(x, 16), "conv_in", self.ch)
         h = self._resnet(h, "down.0.block.0")
         ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True)
         out = torch.empty_like(x)
@@ -384,7 +387,7 @@ class VAEDecoderadaptor(_Adaptor):
     kind = "decoder"
 
     def _forward_one(self, z: Tensor) -> Tensor:
-        h = self._conv(ops.planar_to_cl(z, 32), "conv_in", self.ch)
+        h = self._conv(ops.planar_to_cl(z, 16), "conv_in", self.ch)
         h = self._resnet(h, "up.0.block.0")
         h = self._resnet(h, "up.0.block.1")
         ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True)

@@ -48,14 +48,27 @@ AR = V.Arith(True)
     (32, 192, 2, 8, 16),      # exactly one tile, NT = 192
     (192, 384, 2, 9, 17),     # ksub = 2, two N tiles of 192
     (384, 32, 1, 16, 32),     # encoder head shape (Cout 32)
+    (16, 96, 3, 20, 24),      # thin input, 4 taps per weight box (3-channel video padded to 16)
+    (32, 128, 2, 17, 40),     # thin input, 2 taps per weight box
+    (48, 64, 2, 16, 16),      # one 64-channel block with 3 k-slices
+    (80, 64, 2, 16, 16),      # 64 + 16 channels
 ])
 def test_conv3d_causal(ops, cin, cout, T, H, W):
     x = _rand((1, cin, T, H, W), 1)
     w = _rand((cout, cin, 3, 3, 3), 2, (cin * 27) ** -0.5)
     b = _rand((cout,), 3, 0.1)
     ref = V.causal_conv3d(x.float(), w, b, AR)
-    y = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda()), b.cuda(), cout, (3, 3, 3), pad=(2, 1, 1))
+    y = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda(), 16 if cin % 32 else 32), b.cuda(), cout, (3, 3, 3),
+                    pad=(2, 1, 1))
     assert rel_err(_ncthw(y), ref) < 3e-3
+    if cin % 32 == 0:          # the per-tap kernel (debug flag 0x10000) must agree bit for bit
+        from more4d_b200 import _lib
+        _lib.lib().m4d_set_debug_flags(0x10000)
+        try:
+            y2 = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda()), b.cuda(), cout, (3, 3, 3), pad=(2, 1, 1))
+        finally:
+            _lib.lib().m4d_set_debug_flags(0)
+        assert rel_err(y2.float(), y.float()) < 2e-3
 
 
 def test_conv_residual_and_pointwise(ops):

@@ -11,6 +11,8 @@ from more4d_b200 import _lib, ops           # noqa: E402
 
 BF16 = torch.bfloat16
 SHAPES = [(96, 96, 4, 720, 1280, 3), (192, 192, 4, 360, 640, 3), (384, 384, 4, 180, 320, 3), (128, 128, 4, 720, 1280, 1)]
+if os.environ.get("PROF_CONV_SHAPES") == "thin":
+    SHAPES = [(16, 128, 4, 720, 1280, 1), (16, 96, 4, 720, 1280, 3), (128, 3, 4, 720, 1280, 1), (96, 3, 4, 720, 1280, 3)]
 
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
@@ -21,5 +23,5 @@ if __name__ == "__main__":
             x = torch.randn(T, H, W, cin, device="cuda", dtype=BF16)
             w = torch.randn(cout, cin, kt, 3, 3, device="cuda", dtype=BF16) * 0.02
             out = torch.empty(T, H, W, cout, device="cuda", dtype=BF16)
-            ops.conv_cl(x, ops.pack_conv_weight(w), None, cout, (kt, 3, 3), pad=(kt - 1, 1, 1), out=out)
+            ops.conv_cl(x, ops.pack_conv_weight(w, 16 if cin % 32 else 32), None, cout, (kt, 3, 3), pad=(kt - 1, 1, 1), out=out)
             torch.cuda.synchronize()
