@@ -118,6 +118,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug only: truncate the block stack (number is then INVALID)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hoist-conditioning", action="store_true",
+                    help="compute the step-invariant context embedding / cross-attention K/V once instead of "
+                         "per step (bit-identical; NOT the default: the reference recomputes them every step)")
     args = ap.parse_args()
 
     import torch
@@ -137,7 +140,8 @@ def main():
                           f"L={L} tokens, CFG batch 2, 1 sample/GPU",
               "parallelism": f"dp{world} (sample-sharded replicas, all-gather of final latents)",
               "l2": "inputs (28 GB weights + GB-scale activations) exceed the 126 MB L2 every step",
-              "layers_override": args.layers or None}
+              "layers_override": args.layers or None,
+              "hoist_conditioning": bool(args.hoist_conditioning)}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -173,7 +177,8 @@ def main():
 
     model = WanTransformer4DModel.from_config(cfg, device=dev)
     synth.fill_module_(model, cfg, seed=0)
-    den = StraGDenoiser(model, guidance_scale=6.0, shift=5.0, num_inference_steps=50)
+    den = StraGDenoiser(model, guidance_scale=6.0, shift=5.0, num_inference_steps=50,
+                        hoist_conditioning=args.hoist_conditioning)
     lat_t = (frames - 1) // 4 + 1
     latent_shape = (1, 16, lat_t, height // 8, width // 8)
     lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True,

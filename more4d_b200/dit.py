@@ -196,25 +196,32 @@ class WanI2VCrossAttention(WanSelfAttention):
             self.v_img = _Param((dim, dim), device=device)
             self.norm_k_img = WanRMSNorm(dim, eps, device=device) if qk_norm else None
 
-    def attend(self, x: Tensor, context: Tensor) -> Tensor:   # type: ignore[override]
-        B, L, C = x.shape
-        n, d = self.num_heads, self.head_dim
-        q = ops.linear(x, self.q.weight, self.q.bias)
-        ops.rmsnorm_rope_(q, self.norm_q.weight if self.qk_norm else None, n, self.eps)
+    def project_context(self, context: Tensor):
+        """K/V of the text (and image) context, t4d:481-483,527-531 — independent of x and of the
+        timestep, i.e. identical on all 50 steps of the loop.  Returns (k, v, k_img, v_img)."""
+        n = self.num_heads
         ctx_txt = context[:, self.clip_tokens:].contiguous() if self.image_branch else context
         k = ops.linear(ctx_txt, self.k.weight, self.k.bias)
         ops.rmsnorm_rope_(k, self.norm_k.weight if self.qk_norm else None, n, self.eps)
         v = ops.linear(ctx_txt, self.v.weight, self.v.bias)
-        Lt = ctx_txt.shape[1]
-        q4 = q.view(B, L, n, d)
-        o = ops.attention(q4, k.view(B, Lt, n, d), v.view(B, Lt, n, d))
+        ki = vi = None
         if self.image_branch:
             ctx_img = context[:, :self.clip_tokens].contiguous()
             ki = ops.linear(ctx_img, self.k_img.weight, self.k_img.bias)
             ops.rmsnorm_rope_(ki, self.norm_k_img.weight if self.qk_norm else None, n, self.eps)
             vi = ops.linear(ctx_img, self.v_img.weight, self.v_img.bias)
-            Li = ctx_img.shape[1]
-            ops.attention(q4, ki.view(B, Li, n, d), vi.view(B, Li, n, d), out=o, accumulate=True)
+        return k, v, ki, vi
+
+    def attend(self, x: Tensor, context: Optional[Tensor], kv=None) -> Tensor:   # type: ignore[override]
+        B, L, C = x.shape
+        n, d = self.num_heads, self.head_dim
+        q = ops.linear(x, self.q.weight, self.q.bias)
+        ops.rmsnorm_rope_(q, self.norm_q.weight if self.qk_norm else None, n, self.eps)
+        k, v, ki, vi = kv if kv is not None else self.project_context(context)
+        q4 = q.view(B, L, n, d)
+        o = ops.attention(q4, k.view(B, -1, n, d), v.view(B, -1, n, d))
+        if ki is not None:
+            ops.attention(q4, ki.view(B, -1, n, d), vi.view(B, -1, n, d), out=o, accumulate=True)
         return o.view(B, L, C)
 
     def forward(self, x, context, context_lens=None, dtype=BF16, t=0):   # type: ignore[override]
@@ -268,7 +275,7 @@ class WanAttentionBlock(nn.Module):
             self.spatial_guidance_self = self.spatial_guidance_ffn = None
 
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens=None, dtype=BF16,
-                t=0, dino_features=None, use_cls_token=False):
+                t=0, dino_features=None, use_cls_token=False, cross_kv=None):
         """x: [B, L, C] fp32 (bf16 accepted and widened); e: [B, 6, C] fp32.  Returns the fp32
         residual stream.  A contiguous fp32 `x` is updated in place and returned."""
         _no_grad_only("WanAttentionBlock")
@@ -283,7 +290,7 @@ class WanAttentionBlock(nn.Module):
         cos, sin = _rope_cache.get(freqs, dev)
         grid = torch.as_tensor(grid_sizes).to(device=dev, dtype=torch.int32).contiguous()
         k_lens = torch.as_tensor(seq_lens).to(device=dev, dtype=torch.int32)
-        context = context.to(BF16)
+        context = None if context is None else context.to(BF16)
 
         feats = None
         if dino_features is not None and dino_features[0] is not None and \
@@ -311,7 +318,7 @@ class WanAttentionBlock(nn.Module):
             n3 = ops.layernorm_modulate(x, self.norm3.weight, self.norm3.bias, eps=self.eps)
         else:
             n3 = x.to(BF16)
-        o = self.cross_attn.attend(n3, context)
+        o = self.cross_attn.attend(n3, context, cross_kv)
         ops.linear(o, self.cross_attn.o.weight, self.cross_attn.o.bias, ops.EPI_GATE_RESIDUAL_F32,
                    out=x, residual=x)
         # FFN, x += y * e5
@@ -364,6 +371,19 @@ class _Config(dict):
     """Minimal stand-in for diffusers' FrozenDict config (`transformer.config.patch_size`,
     `.get("add_ref_conv")` are read by the pipeline, pctl:703,737)."""
     __getattr__ = dict.get
+
+
+class Conditioning:
+    """Step-invariant products of `WanTransformer4DModel.precompute_conditioning`."""
+
+    def __init__(self, context: Tensor, cross_kv):
+        self.context = context            # [B, 257 + text_len, C] bf16
+        self.cross_kv = cross_kv          # per block: (k, v, k_img, v_img), each [B, Lctx, C] bf16
+
+    def tail(self, h: int) -> "Conditioning":
+        """The conditional half of a CFG batch (cfg_skip, cfg_optimization.py:9-35)."""
+        cut = lambda t: None if t is None else t[h:]
+        return Conditioning(self.context[h:], [tuple(cut(t) for t in kv) for kv in self.cross_kv])
 
 
 class WanTransformer4DModel(nn.Module):
@@ -485,8 +505,20 @@ class WanTransformer4DModel(nn.Module):
             ctx = torch.cat([self.img_emb(clip_fea.to(device=dev, dtype=BF16)), ctx], dim=1)
         return ctx
 
+    def precompute_conditioning(self, context: Sequence[Tensor], clip_fea: Optional[Tensor]) -> "Conditioning":
+        """Everything in the forward that depends only on the prompt / CLIP tokens: the context
+        embedding (t4d:1175-1184) and every block's cross-attention K/V (t4d:481-483,527-531).
+        The reference recomputes them on each of the 50 steps (pctl:796 calls the whole forward);
+        they are bit-identical across steps, so `forward(..., conditioning=c)` reuses them
+        (SURVEY §8f rank 1).  ~31 MB per block at 14B dims, batch 2."""
+        _no_grad_only("WanTransformer4DModel")
+        dev = self.patch_embedding.weight.device
+        ctx = self.embed_context([c.to(device=dev, dtype=BF16) for c in context], clip_fea)
+        return Conditioning(ctx, [blk.cross_attn.project_context(ctx) for blk in self.blocks])
+
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera=None, full_ref=None,
-                subject_ref=None, cond_flag=True, first_frame=None, guidance_features=None):
+                subject_ref=None, cond_flag=True, first_frame=None, guidance_features=None,
+                conditioning: Optional["Conditioning"] = None):
         """Same call surface as t4d:1046-1060.  x: [B, 16, T, h, w] (tensor or list of
         [16, T, h, w]); y: [B, 48, T, h, w]; t: [B]; context: list of [Lt, text_dim];
         clip_fea: [B, 257, 1280]; full_ref: [B, 16, h, w].  Returns [B, 16, T, h, w] bf16.
@@ -505,16 +537,20 @@ class WanTransformer4DModel(nn.Module):
                 self.current_steps >= self.num_inference_steps * (1 - self.cfg_skip_ratio))
         if skip:
             h = bs // 2
+            if conditioning is not None:
+                conditioning = conditioning.tail(h)
             x, t, context = x[h:], t[h:], context[h:]
             clip_fea = None if clip_fea is None else clip_fea[h:]
             y = None if y is None else y[h:]
             full_ref = None if full_ref is None else full_ref[h:]
-        out = self._forward(x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag)
+        out = self._forward(x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag,
+                            conditioning)
         if skip:
             out = torch.cat([out, out], dim=0)
         return out
 
-    def _forward(self, x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag=True):
+    def _forward(self, x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag=True,
+                 conditioning=None):
         dev = self.patch_embedding.weight.device
         if isinstance(x, (list, tuple)):
             x = torch.stack(list(x))
@@ -550,7 +586,10 @@ class WanTransformer4DModel(nn.Module):
             for b in range(B):
                 ops.linear(rcols[b], rw, self.ref_conv.bias, ops.EPI_F32, out=xs[b, :ref_len])
         e, e0 = self.embed_time(t.to(dev))
-        ctx = self.embed_context([c.to(device=dev, dtype=BF16) for c in context], clip_fea)
+        if conditioning is not None:
+            ctx = None
+        else:
+            ctx = self.embed_context([c.to(device=dev, dtype=BF16) for c in context], clip_fea)
         seq_lens = torch.full((B,), n_tok, device=dev, dtype=torch.int32)
         grid_sizes = torch.tensor([grid] * B, device=dev, dtype=torch.int32)
         run_blocks = True
@@ -563,9 +602,10 @@ class WanTransformer4DModel(nn.Module):
             else:
                 ori = xs.clone().cpu() if tc.offload else xs.clone()
         if run_blocks:
-            for blk in self.blocks:
+            for i, blk in enumerate(self.blocks):
                 xs = blk(xs, e0, seq_lens, grid_sizes, self.freqs, ctx, None, BF16, t,
-                         dino_features=guidance_features, use_cls_token=self.use_cls_token)
+                         dino_features=guidance_features, use_cls_token=self.use_cls_token,
+                         cross_kv=None if conditioning is None else conditioning.cross_kv[i])
             if tc is not None:
                 res = (xs.cpu() - ori) if tc.offload else (xs - ori)
                 if cond_flag:

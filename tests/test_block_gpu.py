@@ -142,3 +142,46 @@ def test_teacache_skips_block_stack():
     assert (n2 - n1) < (n1 - n0) // 2
     assert torch.isfinite(y2.float()).all() and y2.shape == y1.shape
     model.disable_teacache()
+
+
+def test_hoisted_conditioning_is_bit_identical():
+    """the context embedding and every block's cross-attention K/V do not
+    depend on the timestep; computing them once (`precompute_conditioning`) must give exactly the
+    outputs of the reference-shaped forward that recomputes them, with fewer launches — also
+    through StraGDenoiser(hoist_conditioning=True) and under cfg_skip."""
+    from more4d_b200 import ops
+    from more4d_b200.dit import WanTransformer4DModel
+    from more4d_b200.pipeline import StraGDenoiser, synthetic_conditioning
+    cfg, grid, seed = WAN_TINY, (2, 2, 3), 13
+    sd = synth.dit_state_dict(cfg, seed)
+    inp = synth.dit_inputs(cfg, grid, 2, seed)
+    model = WanTransformer4DModel.from_config(cfg, device="cuda")
+    model.load_state_dict(sd, strict=True)
+    ctx = [c.cuda() for c in inp["context"]]
+    kw = dict(x=inp["x"].cuda(), y=inp["y"].cuda(), t=inp["t"].cuda(), context=ctx, seq_len=inp["seq_len"],
+              clip_fea=inp["clip_fea"].cuda(), full_ref=inp["full_ref"].cuda())
+    with torch.no_grad():
+        n0 = ops.launches()
+        y_ref = model(**kw)
+        n1 = ops.launches()
+        pre = model.precompute_conditioning(ctx, inp["clip_fea"].cuda())
+        n2 = ops.launches()
+        y_pre = model(conditioning=pre, **kw)
+        n3 = ops.launches()
+        assert torch.equal(y_ref, y_pre)
+        assert (n3 - n2) < (n1 - n0)
+        model.enable_cfg_skip(0.5, 10)
+        model.current_steps = 9
+        assert torch.equal(model(conditioning=pre, **kw), model(**kw))
+        model.disable_cfg_skip()
+        # loop level: two steps of the denoiser, with and without hoisting
+        shape = (1, 16, grid[0], 2 * grid[1], 2 * grid[2])
+        outs = []
+        for hoist in (False, True):
+            lat, cond = synthetic_conditioning(shape, seed=3, device="cuda", text_dim=cfg.text_dim,
+                                               clip_dim=cfg.clip_dim)
+            den = StraGDenoiser(model, num_inference_steps=4, hoist_conditioning=hoist)
+            for i in range(2):
+                den.step(lat, i, cond)
+            outs.append(lat.clone())
+        assert torch.equal(outs[0], outs[1])

@@ -34,7 +34,9 @@ def _worker(rank, world, port, n, q):
         lats, conds = _inputs(n)
         out = mdist.denoise_sharded(_step, lats, conds, steps=[0, 1, 2])
         u, t = mdist.cfg_split_noise(lambda br: torch.full((2, 3), float(br + 1)))
-        q.put((rank, [o.float() for o in out], u, t, mdist.shard_indices(n)))
+        # plain numpy through the queue: torch tensors travel as file descriptors served by the
+        # child, which may have exited before the parent reads them
+        q.put((rank, [o.float().numpy() for o in out], u.numpy(), t.numpy(), mdist.shard_indices(n)))
     finally:
         dist.destroy_process_group()
 
@@ -62,5 +64,6 @@ def test_sample_sharding_matches_single_rank():
         for rank, out, u, t, _ in res:
             assert len(out) == n
             for a, b in zip(out, ref):
-                assert torch.equal(a, b.float())
-            assert torch.equal(u, torch.full((2, 3), 1.0)) and torch.equal(t, torch.full((2, 3), 2.0))
+                assert torch.equal(torch.from_numpy(a), b.float())
+            assert torch.equal(torch.from_numpy(u), torch.full((2, 3), 1.0))
+            assert torch.equal(torch.from_numpy(t), torch.full((2, 3), 2.0))
