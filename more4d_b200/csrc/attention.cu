@@ -40,6 +40,7 @@ constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024;
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
 constexpr int A_DEFAULT_VAR = 0;
 constexpr int A_DEFAULT_K64 = 0;              // 1: use the double-buffered 64-key-step kernel
+constexpr int A_DEFAULT_SPLIT = 0;            // 1: 16-softmax-warp kernel (two threads per row)
 constexpr int A_DEFAULT_PACE = 0;             // FFMA2 pacing distance in pairs (exp_pairs)
 constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe (measured: 0 is fastest)
 
@@ -763,6 +764,327 @@ attn_fwd_d128_k64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 10) tmem_dealloc<512>(tmem_base);
 }
 
+
+// =======================================================================================
+// Variant "split": SIXTEEN softmax warps — two threads per query row, 64 keys each.
+//
+// In the kernel at the top one thread owns a whole 128-key row, and the per-tile chain
+// S ready -> [tcgen05.ld, max pass, scale, 128 EX2] -> P ready -> PV -> QK -> S ready is what
+// bounds the period: sampling (profiles/attn_r01c.md) shows 1760 busy clocks per tile-step in
+// the softmax warps, of which only 1024 are MUFU-bound; the rest is the serial in-order
+// instruction stream of ONE warp per scheduler (max pass 235, FFMA2 block 235, loads / stores /
+// barriers).  Here the two warpgroups of a tile split the columns: the MUFU work per tile is
+// unchanged (the two warps of a scheduler share the pipe) but every other part of the chain is
+// done by twice as many threads, with the same total instruction count — the kernel is
+// power-capped, so trading energy for cycles (polynomial exp2, pacing) does not pay, shortening
+// the chain at equal work should.  MEASURED: it does not (profiles/attn_split_r01.md: 7.22 M vs
+// 6.63 M cycles, tensor pipe 65 % vs 71 %, 1170 vs 1260-1290 TF/s): the partner warps w and
+// w + 4 sit on the SAME scheduler, whose issue slot and MUFU were the busy resources, so the
+// per-tile softmax takes as long as before plus the exchange.  Kept as a debug variant
+// (flags 0x6000000), default off.  Costs: one 64-thread named barrier + a 2-float exchange per
+// row and step for the row max, and 104 instead of 208 registers per softmax thread.
+// Warps: 0-7 tile 0 (0-3 keys 0-63, 4-7 keys 64-127), 8-15 tile 1, 16 TMA, 17 MMA, 18 TMEM.
+// =======================================================================================
+constexpr int C_THREADS = 640;
+constexpr int C_XCH_FLOATS = 2 * 2 * 2 * 128 + 2 * 2 * 128;      // max exchange (double-buffered) + l exchange
+constexpr int C_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + C_XCH_FLOATS * 4 + 256 + 1024;
+
+__global__ void __launch_bounds__(C_THREADS, 1)
+attn_fwd_d128_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + A_NQ * A_TILE_BYTES;
+  uint8_t* sV = sK + A_KS * A_TILE_BYTES;
+  float* xch = reinterpret_cast<float*>(sV + A_VS * A_TILE_BYTES);      // [parity][tile][half][row]
+  float* lxch = xch + 2 * 2 * 2 * 128;                                 // [tile][half][row]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + C_XCH_FLOATS);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* k_full = q_full + 1;        // A_KS
+  uint64_t* k_empty = k_full + A_KS;    // A_KS
+  uint64_t* v_full = k_empty + A_KS;    // A_VS
+  uint64_t* v_empty = v_full + A_VS;    // A_VS
+  uint64_t* s_full = v_empty + A_VS;    // 2
+  uint64_t* p_ready = s_full + 2;       // [t * 2 + half]
+  uint64_t* o_final = p_ready + 4;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+
+  int kv_len = p.Lk;
+  if (p.k_lens != nullptr) {
+    int kl = p.k_lens[b];
+    kv_len = kl < kv_len ? kl : kv_len;
+  }
+  if (kv_len < 1) kv_len = 1;
+  const int n_kv = (kv_len + A_BKV - 1) / A_BKV;
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 17 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < A_KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < A_VS; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_ready[2 * t], 128);
+      mbar_init(&p_ready[2 * t + 1], 128);
+      mbar_init(&o_final[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 18) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 16) {
+    // ------------------------------------------------------------------ data movement + MMA
+    // setmaxnreg.inc only draws on registers released by setmaxnreg.dec in the same CTA: the
+    // 4 x 128 x (104 - 96) = 4096 the softmax warpgroups ask for must be covered by this
+    // warpgroup's 128 x (96 - 56) = 5120 (with dec<80> the last inc blocks forever)
+    reg_dec<56>();
+    if (warp == 16 && lane == 0) {
+      mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
+      for (int t = 0; t < A_NQ; ++t)
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sQ + t * A_TILE_BYTES + h * A_HALF_BYTES, &tmQ, q_full, h * 64, head,
+                      q_blk * (A_NQ * A_BQ) + t * A_BQ, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int sk = j % A_KS, sv = j % A_VS;
+        mbar_wait(&k_empty[sk], ((j / A_KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[sk], A_TILE_BYTES);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sK + sk * A_TILE_BYTES + h * A_HALF_BYTES, &tmK, &k_full[sk], h * 64, head,
+                      j * A_BKV, b);
+        mbar_wait(&v_empty[sv], ((j / A_VS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], A_TILE_BYTES);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sV + sv * A_TILE_BYTES + h * A_HALF_BYTES, &tmV, &v_full[sv], h * 64, head,
+                      j * A_BKV, b);
+      }
+    } else if (warp == 17) {
+      // same issue scheme as attn_fwd_d128_kernel: converged warp, one elected lane
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
+      constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t k_lo = ((smem_u32(sK) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t v_lo = ((smem_u32(sV) >> 4) & 0x3FFF) | ((A_HALF_BYTES >> 4) << 16);
+      const uint32_t tS0 = tmem_base, tO0 = tmem_base + 256;
+      auto dp = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      auto issue_qk = [&](int t, int sk) {
+        const uint32_t a_lo = q_lo + t * (A_TILE_BYTES >> 4), b_lo = k_lo + sk * (A_TILE_BYTES >> 4);
+#pragma unroll
+        for (int kk = 0; kk < A_D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * (A_HALF_BYTES >> 4) + (kk & 3) * 2;
+          umma_ss(tS0 + t * 128, dp(a_lo + off, HI), dp(b_lo + off, HI), idesc_qk, kk != 0);
+        }
+      };
+      auto issue_pv_tile = [&](int t, int sv, int j, bool leader) {
+        const uint32_t b_lo = v_lo + sv * (A_TILE_BYTES >> 4);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          mbar_wait(&p_ready[2 * t + sl], j & 1);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const int kk = sl * 4 + k4;
+              umma_ts(tO0 + t * 128, tS0 + t * 128 + kk * 8, dp(b_lo + kk * (2048 >> 4), HI), idesc_pv,
+                      !(j == 0 && kk == 0));
+            }
+          }
+          __syncwarp();
+        }
+      };
+      const bool leader = elect_one();
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (leader) {
+        issue_qk(0, 0);
+        umma_commit(&s_full[0]);
+        issue_qk(1, 0);
+        umma_commit(&s_full[1]);
+        umma_commit(&k_empty[0]);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        const int sv = j % A_VS;
+        const bool last = (j + 1 == n_kv);
+        const int sk = (j + 1) % A_KS;
+        mbar_wait(&v_full[sv], (j / A_VS) & 1);
+        issue_pv_tile(0, sv, j, leader);
+        if (!last) mbar_wait(&k_full[sk], ((j + 1) / A_KS) & 1);
+        tc_fence_after();
+        if (leader) {
+          if (last) {
+            umma_commit(&o_final[0]);
+          } else {
+            issue_qk(0, sk);
+            umma_commit(&s_full[0]);
+          }
+        }
+        __syncwarp();
+        issue_pv_tile(1, sv, j, leader);
+        if (leader) {
+          umma_commit(&v_empty[sv]);
+          if (last) {
+            umma_commit(&o_final[1]);
+          } else {
+            issue_qk(1, sk);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[sk]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    reg_inc<104>();
+    const int t = warp >> 3;                       // query tile
+    const int hf = (warp >> 2) & 1;                // key half of the 128-key step
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;              // row in tile == TMEM lane
+    const int pair_bar = 1 + t * 4 + quad;         // named barrier shared with the partner warp
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tO = tmem_base + lane_base + 256 + t * 128 + hf * 64;
+    const float c = p.scale_log2;
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      tmem_ld32(tS + hf * 64, s);
+      tmem_ld32(tS + hf * 64 + 32, s + 32);
+      tmem_ld_wait();
+      reg_fence32(s);
+      reg_fence32(s + 32);
+      const int valid = kv_len - j * A_BKV - hf * 64;      // keys of this half that exist
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = 0xFF800000u;              // -inf
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int i = 4; i < 60; i += 8) {
+        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+      }
+      mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
+      mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // row max over both halves: exchange with the partner thread (same row, other key half).
+      // The barrier also orders the partner's tcgen05.ld of S before this thread's P store,
+      // which overwrites S columns the partner reads.
+      float* xs = xch + (((j & 1) * 2 + t) * 2) * 128;
+      xs[hf * 128 + row] = mx;
+      named_bar_sync(pair_bar, 64);
+      mx = fmaxf(mx, xs[(hf ^ 1) * 128 + row]);
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const float m_new = fmaxf(m_used, mx);
+        const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, grow)) {              // identical in the partner warp
+          const float f = fast_exp2((m_used - m_new) * c);
+          m_used = m_new;
+          l_sum *= f;
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {                 // this half's 64 columns of O
+            uint32_t o[32];
+            tmem_ld32(tO + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tO + cc * 32, o);
+          }
+          tmem_st_wait();
+          named_bar_sync(pair_bar, 64);                    // both halves of O rescaled before any PV
+        }
+      }
+      const float neg_mc = -m_used * c;
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t ph[32];
+      exp_pairs<0, 0, 32, 0>(s, ph, c, neg_mc, l0, l1);
+      tmem_st32(tS + hf * 32, ph);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[2 * t + hf]);
+      l_sum += l0 + l1;
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global (this half's 64 channels)
+    float* ls = lxch + t * 2 * 128;
+    ls[hf * 128 + row] = l_sum;
+    named_bar_sync(pair_bar, 64);
+    l_sum += ls[(hf ^ 1) * 128 + row];
+    mbar_wait(&o_final[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
+    const bool row_ok = q_row < p.Lq;
+    bf16* orow = p.out + static_cast<long long>(b) * p.out_stride_b +
+                 static_cast<long long>(q_row) * p.out_stride_l + head * A_D + hf * 64;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tO + cc * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
+          if (p.accumulate) {
+            const uint4 prev = *dst;
+            const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
+              v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+          }
+          uint4 ov;
+          ov.x = pack_bf16(v[0], v[1]);
+          ov.y = pack_bf16(v[2], v[3]);
+          ov.z = pack_bf16(v[4], v[5]);
+          ov.w = pack_bf16(v[6], v[7]);
+          *dst = ov;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 18) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace m4d
 
 using namespace m4d;
@@ -821,9 +1143,17 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
     kern = (var & 1) ? attn_fwd_d128_kernel<2, 1, 0> : (pace ? attn_fwd_d128_kernel<2, 0, 4> : attn_fwd_d128_kernel<2, 0, 0>);
   }
   int smem_bytes = A_SMEM_BYTES;
+  int threads = A_THREADS;
   if (k64) {
     kern = attn_fwd_d128_k64_kernel;
     smem_bytes = B_SMEM_BYTES;
+  }
+  // debug flags 0x4000000: explicit choice, bit 0x2000000 = split-softmax kernel
+  const bool split = (g_debug_flags & 0x4000000) ? ((g_debug_flags & 0x2000000) != 0) : (A_DEFAULT_SPLIT != 0);
+  if (split && !k64 && !(g_debug_flags & 0x100)) {
+    kern = attn_fwd_d128_split_kernel;
+    smem_bytes = C_SMEM_BYTES;
+    threads = C_THREADS;
   }
   if (kern == nullptr) return M4D_ERR_UNSUPPORTED;
   rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
@@ -842,7 +1172,7 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
   p.accumulate = accumulate;
   p.flags = g_debug_flags;
   dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
-  kern<<<grid, A_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, threads, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
   M4D_CHECK_LAUNCH("attn_fwd_d128_kernel");
   return M4D_OK;
 }

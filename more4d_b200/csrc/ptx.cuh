@@ -232,6 +232,9 @@ __device__ __forceinline__ void tmem_st_wait() {
 }
 
 // ------------------------------------------------------------------ misc
+// setmaxnreg: .inc blocks until enough registers have been RELEASED BY .dec IN THE SAME CTA —
+// registers the SM never handed to the CTA do not count (measured: a kernel whose incs exceeded
+// its decs deadlocked although the SM had free registers).
 template <int REGS>
 __device__ __forceinline__ void reg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));

@@ -185,17 +185,20 @@ def gemm2_k():
 def attn_sweep():
     """Polynomial-exp2 share sweep (debug flags 0x10 | PP) at the bench shape + parity."""
     ar = O.Arith(True)
-    q, k, v = rnd((1, 300, 2, 128), 1), rnd((1, 300, 2, 128), 2), rnd((1, 300, 2, 128), 3)
+    q, k, v = rnd((1, 300, 2, 128), 1, 2.0), rnd((1, 300, 2, 128), 2, 2.0), rnd((1, 300, 2, 128), 3)
     ref = O.attention(q, k, v, None, ar)
     B, L, N = 2, 50400, 40
     Q, K, V = (torch.randn(B, L, N, 128, device="cuda", dtype=BF16) for _ in range(3))
     out = torch.empty_like(Q)
     fl = 4.0 * B * N * L * L * 128
-    variants = [(0, 0, 0), (0, 0, 4), (0, 0, 2), (0, 0, 6), (2, 0, 4), (0, 0, 0), (0, 0, 4)]
+    variants = [(0, 0, 0, 0), (0, 0, 0, 1), (0, 0, 0, 0), (0, 0, 0, 1)]     # (PP, VAR, PACE, split)
     if len(sys.argv) > 2:
         variants = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]]
-    for pp, var, pace in variants:
-        _lib.lib().m4d_set_debug_flags(0x200 | 0x100 | (pp << 4) | var | 0x1000000 | (pace << 20))
+    for pp, var, pace, split in variants:
+        if split:
+            _lib.lib().m4d_set_debug_flags(0x4000000 | 0x2000000)
+        else:
+            _lib.lib().m4d_set_debug_flags(0x4000000 | 0x200 | 0x100 | (pp << 4) | var | 0x1000000 | (pace << 20))
         o = ops.attention(q.cuda(), k.cuda(), v.cuda())
         e = rel(o.float().cpu(), ref)
         ops.attention(Q, K, V, out=out)
@@ -208,7 +211,7 @@ def attn_sweep():
             e_.record(); torch.cuda.synchronize()
             ts.append(s_.elapsed_time(e_))
         ms = min(ts)
-        print(f"PP={pp} VAR={var} PACE={pace}: parity rel={e:.3e}  {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s (all: {[round(t,1) for t in ts]})", flush=True)
+        print(f"PP={pp} VAR={var} PACE={pace} split={split}: parity rel={e:.3e}  {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s (all: {[round(t,1) for t in ts]})", flush=True)
     _lib.lib().m4d_set_debug_flags(0)
 
 
