@@ -46,6 +46,10 @@ WAN_1_3B = DiTConfig(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30)
 # (clip_dim / clip_tokens stay 1280 / 257: the reference hard-codes both, t4d:520,938)
 WAN_TINY = DiTConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128,
                      text_len=32)
+# 4D-ViSM stage (Wan2.1-Fun-InP backbone, WanTransformer3DModel): x 16 + mask 4 + masked-video 16
+# input channels (pipeline_wan_fun_inpaint.py:707-713), no reference-frame conv
+WAN_14B_INP = DiTConfig(in_dim=36, add_ref_conv=False)
+WAN_TINY_INP = WAN_TINY.with_(in_dim=36, add_ref_conv=False)
 
 
 def token_grid(frames: int, height: int, width: int, cfg: DiTConfig = WAN_14B,

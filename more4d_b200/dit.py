@@ -617,3 +617,43 @@ class WanTransformer4DModel(nn.Module):
         if tc is not None:
             tc.step_done(cond_flag)
         return out
+
+
+class WanTransformer3DModel(WanTransformer4DModel):
+    """MoRe4D/models/wan_transformer3d.py:725-1511 — the Wan2.1-Fun-InP backbone of the 4D-ViSM
+    stage (scripts/inference/infer.py:935-994).  File-level diff against wan_transformer4d.py:
+    the same blocks, embeddings, RoPE, head and state-dict keys, without the Motion-Perception
+    branch (no `spatial_guidance_*` parameters, no `first_frame`); the oracle reproduces the real
+    class to 2e-7 (tests/test_oracle_vs_golden.py).  Same constructor arguments as t3d:735-759."""
+
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048,
+                 ffn_dim=8192, freq_dim=256, text_dim=4096, out_dim=16, num_heads=16,
+                 num_layers=32, window_size=(-1, -1), qk_norm=True, cross_attn_norm=True, eps=1e-6,
+                 in_channels=16, hidden_size=2048, add_control_adapter=False,
+                 in_dim_control_adapter=24, add_ref_conv=False, in_dim_ref_conv=16,
+                 cross_attn_type=None, device=None):
+        super().__init__(model_type=model_type, patch_size=patch_size, text_len=text_len, in_dim=in_dim,
+                         dim=dim, ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim,
+                         num_heads=num_heads, num_layers=num_layers, window_size=window_size,
+                         qk_norm=qk_norm, cross_attn_norm=cross_attn_norm, eps=eps,
+                         in_channels=in_channels, hidden_size=hidden_size,
+                         add_control_adapter=add_control_adapter,
+                         in_dim_control_adapter=in_dim_control_adapter, add_ref_conv=add_ref_conv,
+                         in_dim_ref_conv=in_dim_ref_conv, cross_attn_type=cross_attn_type,
+                         use_spatial_guidance=False, device=device)
+
+    @classmethod
+    def from_config(cls, cfg: DiTConfig, device=None) -> "WanTransformer3DModel":
+        return cls(model_type=cfg.model_type, patch_size=cfg.patch_size, text_len=cfg.text_len,
+                   in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim, freq_dim=cfg.freq_dim,
+                   text_dim=cfg.text_dim, out_dim=cfg.out_dim, num_heads=cfg.num_heads,
+                   num_layers=cfg.num_layers, qk_norm=cfg.qk_norm,
+                   cross_attn_norm=cfg.cross_attn_norm, eps=cfg.eps, add_ref_conv=cfg.add_ref_conv,
+                   in_dim_ref_conv=cfg.in_dim_ref_conv, device=device)
+
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, y_camera=None, full_ref=None,
+                subject_ref=None, cond_flag=True, conditioning=None):                 # t3d:966-978
+        return super().forward(x, t, context, seq_len, clip_fea=clip_fea, y=y, y_camera=y_camera,
+                               full_ref=full_ref, subject_ref=subject_ref, cond_flag=cond_flag,
+                               conditioning=conditioning)
+

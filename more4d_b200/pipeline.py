@@ -75,29 +75,31 @@ class StraGDenoiser:
         _, _, T, h, w = latents.shape
         return int(np.ceil((h * w) / (ps[1] * ps[2]) * T))
 
-    @torch.no_grad()
-    def step(self, latents: Tensor, i: int, cond: StraGConditioning) -> Tensor:
-        """Advance `latents` ([1, 16, T, h, w] bf16, CUDA, updated in place) by scheduler step i."""
-        tr = self.transformer
-        tr.current_steps = i
-        x = torch.cat([latents] * 2)                                                 # pctl:751
+    def _model_inputs(self, cond) -> dict:
+        """Conditioning tensors of one CFG-doubled forward (pctl:751-794)."""
         start = torch.zeros_like(cond.control_latents)                               # start_image_latentes_conv_in
         parts = [cond.control_latents, start]
         if cond.depth_latents is not None:
             parts.append(cond.depth_latents)
         y1 = torch.cat(parts, dim=1)                                                 # pctl:762-777
-        y = torch.cat([y1] * 2)
-        clip = torch.cat([cond.clip_context] * 2)
         ref = None if cond.ref_latents is None else torch.cat([cond.ref_latents] * 2)
+        return dict(y=torch.cat([y1] * 2), full_ref=ref, clip_fea=torch.cat([cond.clip_context] * 2))
+
+    @torch.no_grad()
+    def step(self, latents: Tensor, i: int, cond) -> Tensor:
+        """Advance `latents` ([1, 16, T, h, w] bf16, CUDA, updated in place) by scheduler step i."""
+        tr = self.transformer
+        tr.current_steps = i
+        x = torch.cat([latents] * 2)                                                 # pctl:751
+        kw = self._model_inputs(cond)
         t = torch.full((2,), float(self.timesteps[i]), device=latents.device, dtype=torch.float32)
         context = [cond.negative_prompt_embeds, cond.prompt_embeds]
         pre = None
         if self.hoist_conditioning:
             if self._hoisted is None or self._hoisted[0] is not cond:
-                self._hoisted = (cond, tr.precompute_conditioning(context, clip))
+                self._hoisted = (cond, tr.precompute_conditioning(context, kw["clip_fea"]))
             pre = self._hoisted[1]
-        noise = tr(x=x, context=context, t=t, seq_len=self.seq_len(latents), y=y, full_ref=ref,
-                   clip_fea=clip, conditioning=pre)                                  # pctl:796
+        noise = tr(x=x, context=context, t=t, seq_len=self.seq_len(latents), conditioning=pre, **kw)  # pctl:796
         dt = float(self.sigmas[i + 1] - self.sigmas[i])
         ops.cfg_euler_step_(latents, noise[0:1], noise[1:2], self.guidance_scale, dt)  # pctl:820-825
         return latents
@@ -112,6 +114,47 @@ class StraGDenoiser:
         for i in (range(self.num_inference_steps) if steps is None else steps):
             self.step(lat, i, c)
         return lat.to("cpu")
+
+
+@dataclass
+class ViSMConditioning:
+    """Step-invariant inputs of the 4D-ViSM (Wan-InP) loop for one sample
+    (pipeline_wan_fun_inpaint.py:612-690)."""
+    mask_latents: Tensor               # [1, 4, T, h, w]   resize_mask(1 - mask_condition)      pinp:642-646
+    masked_video_latents: Tensor       # [1, 16, T, h, w]  vae.encode(masked video)             pinp:653-664
+    clip_context: Tensor               # [1, 257, 1280]
+    prompt_embeds: Tensor              # [Lp, 4096]
+    negative_prompt_embeds: Tensor     # [Ln, 4096]
+
+    def to(self, device) -> "ViSMConditioning":
+        mv = lambda t: t.to(device=device, dtype=BF16, non_blocking=True)
+        return ViSMConditioning(mv(self.mask_latents), mv(self.masked_video_latents), mv(self.clip_context),
+                                mv(self.prompt_embeds), mv(self.negative_prompt_embeds))
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * 2 for t in (self.mask_latents, self.masked_video_latents, self.clip_context,
+                                           self.prompt_embeds, self.negative_prompt_embeds))
+
+
+class ViSMDenoiser(StraGDenoiser):
+    """The 4D-ViSM denoise loop (pipeline_wan_fun_inpaint.py:693-743) on the same kernels: the
+    DiT call differs from 4D-STraG only in its conditioning — y = cat(mask latents [4], masked-
+    video latents [16]) (pinp:707-713), no reference frame — and runs WanTransformer3DModel."""
+
+    def _model_inputs(self, cond: ViSMConditioning) -> dict:
+        y1 = torch.cat([cond.mask_latents, cond.masked_video_latents], dim=1)
+        return dict(y=torch.cat([y1] * 2), full_ref=None, clip_fea=torch.cat([cond.clip_context] * 2))
+
+
+def synthetic_visim_conditioning(latent_shape, seed: int = 0, device="cpu", prompt_tokens: int = 32,
+                                 negative_tokens: int = 1, text_dim: int = 4096, clip_dim: int = 1280):
+    """Synthetic latents + ViSM conditioning (denoise part)."""
+    g = torch.Generator().manual_seed(seed)
+    _, c, T, h, w = latent_shape
+    rn = lambda *shape: torch.randn(*shape, generator=g).to(BF16).to(device)
+    mask = (torch.rand(1, 4, T, h, w, generator=g) < 0.5).to(BF16).to(device)
+    return rn(1, c, T, h, w), ViSMConditioning(mask, rn(1, 16, T, h, w), rn(1, 257, clip_dim),
+                                               rn(prompt_tokens, text_dim), rn(negative_tokens, text_dim))
 
 
 def synthetic_conditioning(latent_shape, seed: int = 0, device="cpu", pin: bool = False,

@@ -129,3 +129,10 @@ def load():
     vae = importlib.import_module("MoRe4D.models.wan_vae")
     traj = importlib.import_module("MoRe4D.models.trajectory_module")
     return t4d, vae, traj
+
+
+def load3d():
+    """The reference's 4D-ViSM backbone module (MoRe4D/models/wan_transformer3d.py)."""
+    load()
+    return importlib.import_module("MoRe4D.models.wan_transformer3d")
+

@@ -112,6 +112,24 @@ def model_case(t4d, name, cfg: DiTConfig, grid, batch, seed):
     print(name, tuple(y.shape), float(y.abs().mean()))
 
 
+def model3d_case(t3d, name, cfg: DiTConfig, grid, batch, seed):
+    """Real WanTransformer3DModel (the 4D-ViSM / Wan-InP backbone): in_dim 36, no reference conv."""
+    sd = synth.dit_state_dict(cfg, seed)
+    m = t3d.WanTransformer3DModel(
+        model_type="i2v", in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim,
+        num_heads=cfg.num_heads, num_layers=cfg.num_layers, text_dim=cfg.text_dim,
+        text_len=cfg.text_len)
+    m.load_state_dict(f32(sd), strict=True)
+    m.eval()
+    inp = synth.dit_inputs(cfg, grid, batch, seed, with_ref=False)
+    y = m(x=inp["x"].float(), t=inp["t"], context=[c.float() for c in inp["context"]],
+          seq_len=inp["seq_len"], clip_fea=inp["clip_fea"].float(), y=inp["y"].float())
+    save_file({"y": y.contiguous(), "x_sum": checksum(inp["x"]),
+               "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))},
+              os.path.join(OUT, name + ".safetensors"))
+    print(name, tuple(y.shape), float(y.abs().mean()))
+
+
 def vae_cases(vae_mod, traj_mod):
     """Real AutoencoderKLWan (chunked encode/decode with the feature cache) and the two
     trajectory adaptors on small clips: 13 frames = 1 + three 4-frame chunks on the encoder
@@ -148,6 +166,10 @@ def vae_cases(vae_mod, traj_mod):
 
 def main():
     t4d, _vae, _traj = ref_import.load()
+    from more4d_b200.config import WAN_TINY_INP
+    model3d_case(ref_import.load3d(), "dit3d_tiny", WAN_TINY_INP, (3, 4, 6), 2, seed=5)
+    if "--only-3d" in sys.argv:
+        return
     vae_cases(_vae, _traj)
     ops_case(t4d)
     tiny = WAN_TINY

@@ -55,3 +55,25 @@ def test_install_vae_and_adaptors():
     if not torch.cuda.is_available():
         with torch.no_grad(), pytest.raises(RuntimeError):
             ref.decode(torch.zeros(1, 16, 1, 4, 4, dtype=torch.bfloat16))
+
+
+def test_install_3d_transformer_visim_backbone():
+    """install() also adopts the 4D-ViSM backbone (wan_transformer3d.WanTransformer3DModel)."""
+    from more4d_b200 import install, synth
+    from more4d_b200.config import WAN_TINY_INP as cfg
+    t3d = ref_import.load3d()
+    ref = t3d.WanTransformer3DModel(model_type="i2v", in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim,
+                                    num_heads=cfg.num_heads, num_layers=cfg.num_layers, text_dim=cfg.text_dim,
+                                    text_len=cfg.text_len).to(torch.bfloat16)
+    ref.load_state_dict(synth.dit_state_dict(cfg, 0), strict=True)
+    install.install(transformer=ref)
+    mine = dict(ref._m4d.named_parameters())
+    assert set(mine) == set(dict(ref.named_parameters()))
+    for name, p in ref.named_parameters():
+        assert mine[name] is p
+    assert ref._m4d.ref_conv is None and ref._m4d.blocks[0].spatial_guidance_self is None
+    inp = synth.dit_inputs(cfg, (3, 4, 6), 2, 0, with_ref=False)
+    if not torch.cuda.is_available():
+        with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+            ref(x=inp["x"], t=inp["t"], context=inp["context"], seq_len=inp["seq_len"],
+                clip_fea=inp["clip_fea"], y=inp["y"])

@@ -85,3 +85,19 @@ def test_model_tiny(golden):
                       full_ref=inp["full_ref"].float())
     assert y.shape == g["y"].shape
     assert rel_err(y, g["y"]) < TOL
+
+
+def test_model3d_tiny(golden):
+    """The 4D-ViSM backbone (WanTransformer3DModel, in_dim 36, no reference conv): the same oracle
+    functions reproduce the REAL 3D class (golden made by tests/golden/make_golden.py)."""
+    from more4d_b200.config import WAN_TINY_INP
+    g = golden("dit3d_tiny")
+    cfg, grid, batch, seed = WAN_TINY_INP, (3, 4, 6), 2, 5
+    sd = synth.dit_state_dict(cfg, seed)
+    assert not any("ref_conv" in k or "spatial_guidance" in k for k in sd)
+    inp = synth.dit_inputs(cfg, grid, batch, seed, with_ref=False)
+    assert torch.allclose(checksum(inp["x"]), g["x_sum"], rtol=1e-6), "RNG drift: regenerate goldens"
+    y = O.dit_forward(sd, cfg, inp["x"].float(), inp["t"], [c.float() for c in inp["context"]],
+                      inp["seq_len"], clip_fea=inp["clip_fea"].float(), y=inp["y"].float(), full_ref=None)
+    assert y.shape == g["y"].shape
+    assert rel_err(y, g["y"]) < TOL
