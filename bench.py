@@ -33,6 +33,8 @@ WORKLOADS = {
     "720p-1.3b": ("WAN_1_3B", 49, 720, 1280),
     "480p-1.3b": ("WAN_1_3B", 49, 480, 832),
     "tiny": ("WAN_TINY", 9, 64, 96),
+    # 4D-ViSM (Wan-InP backbone) denoise part of BASELINE config 5 — NOT the headline metric
+    "visim-368p-14b": ("WAN_14B_INP", 49, 368, 512),
 }
 METRIC = "4D-STraG denoise-step latents/sec @49x720p"
 UNIT = "latent-steps/s"
@@ -130,12 +132,13 @@ def main():
     cfg = getattr(mcfg, preset)
     if args.layers:
         cfg = cfg.with_(num_layers=args.layers)
-    grid = mcfg.token_grid(frames, height, width, cfg)
+    visim = args.workload.startswith("visim")
+    grid = mcfg.token_grid(frames, height, width, cfg, with_ref=not visim)
     L = grid[0] * grid[1] * grid[2]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: Wan2.1-14B-Control dims (C{cfg.dim} F{cfg.ffn_dim} "
+    config = {"workload": f"{args.workload}: Wan2.1-14B-{'InP' if visim else 'Control'} dims (C{cfg.dim} F{cfg.ffn_dim} "
                           f"{cfg.num_heads}h x{cfg.num_layers}L) {frames}x{height}x{width}, "
                           f"L={L} tokens, CFG batch 2, 1 sample/GPU",
               "parallelism": f"dp{world} (sample-sharded replicas, all-gather of final latents)",
@@ -166,8 +169,9 @@ def main():
     # ------------------------------------------------------------------ our arm (B200)
     import torch.distributed as dist
     from more4d_b200 import dist as mdist, ops, synth
-    from more4d_b200.dit import WanTransformer4DModel
-    from more4d_b200.pipeline import StraGDenoiser, synthetic_conditioning
+    from more4d_b200.dit import WanTransformer3DModel, WanTransformer4DModel
+    from more4d_b200.pipeline import (StraGDenoiser, ViSMDenoiser, synthetic_conditioning,
+                                      synthetic_visim_conditioning)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -175,14 +179,20 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 
-    model = WanTransformer4DModel.from_config(cfg, device=dev)
+    model = (WanTransformer3DModel if visim else WanTransformer4DModel).from_config(cfg, device=dev)
     synth.fill_module_(model, cfg, seed=0)
-    den = StraGDenoiser(model, guidance_scale=6.0, shift=5.0, num_inference_steps=50,
-                        hoist_conditioning=args.hoist_conditioning)
+    den = (ViSMDenoiser if visim else StraGDenoiser)(model, guidance_scale=6.0, shift=5.0,
+                                                     num_inference_steps=50,
+                                                     hoist_conditioning=args.hoist_conditioning)
     lat_t = (frames - 1) // 4 + 1
     latent_shape = (1, 16, lat_t, height // 8, width // 8)
-    lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True,
-                                                 text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
+    if visim:
+        lat_host, cond_host = synthetic_visim_conditioning(latent_shape, seed=rank, device="cpu",
+                                                           text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
+        lat_host = lat_host.pin_memory()
+    else:
+        lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True,
+                                                     text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
     lat = lat_host.to(dev)
     cond = cond_host.to(dev)
     gathered = None
