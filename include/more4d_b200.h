@@ -204,6 +204,20 @@ int m4d_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in,
  * (wan_transformer4d.py:746-748,781). */
 int m4d_silu_bf16(const float* x, void* out, long long n, void* stream);
 
+/* ---- stage hand-off: point-cloud projection with a z-buffer ---- */
+
+/* render_with_project, scripts/inference/infer.py:222-258 (project() MoRe4D/utils/project_utils.py:
+ * 47-71; torch.unique + index_reduce_('amin') z-buffer :238-241; torch_scatter mean :246; pad,
+ * [W,H,3]->[H,W,3] transpose, uint8 truncation and hole mask :247-256) as three passes.
+ * points, colors: DEVICE fp32 [N, 3] (colours 0..255); world2cam: HOST fp32 [4,4] row-major =
+ * extrinsic.inverse(); intrinsic: HOST fp32 [3,3] (normalised image coordinates).  Outputs:
+ * image DEVICE uint8 [H, W, 3], mask DEVICE uint8 [H, W] (1 = no point landed there).
+ * workspace: DEVICE, 16-byte aligned, >= m4d_project_points_workspace(N, H, W) bytes. */
+long long m4d_project_points_workspace(long long N, int H, int W);
+int m4d_project_points(const float* points, const float* colors, const float* world2cam,
+                       const float* intrinsic, long long N, int H, int W, unsigned char* image,
+                       unsigned char* mask, void* workspace, long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "m4d_groupnorm_swish_cl": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "m4d_softmax_rows": (c_int, [_P, _P, _I, _I, _L, _L, _F, _P]),
     "m4d_transpose_bf16": (c_int, [_P, _P, _I, _I, _L, _L, _P]),
+    "m4d_project_points_workspace": (c_longlong, [_L, _I, _I]),
+    "m4d_project_points": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P]),
 }
 
 _lib = None

@@ -177,3 +177,28 @@ def fill_module_(module, cfg: DiTConfig, seed: int = 0) -> None:
         for key, p in sd.items():
             shape, std, mean = specs[key]
             p.copy_(_randn(seed, key, shape, std, p.device, p.dtype, mean))
+
+
+def point_cloud(H: int, W: int, seed: int = 0, tilt: float = 0.0):
+    """Synthetic stage-1 output for the hand-off renderer (scripts/inference/infer.py:398-444): one
+    3-D point per pixel of an H x W frame, back-projected with random depth, integer-valued
+    colours (uint8 image), a camera translated / rotated by `tilt` so that points collide in the
+    z-buffer, leave the frustum and land behind the camera.  Returns (points [N,3] fp32,
+    colors [N,3] fp32 in 0..255, extrinsic [4,4] cam->world, intrinsic [3,3])."""
+    import math
+    g = torch.Generator().manual_seed(1000 + seed)
+    from .render import get_intrinsic_matrix
+    K = get_intrinsic_matrix(H, W)
+    v, u = torch.meshgrid((torch.arange(H) + 0.5) / H, (torch.arange(W) + 0.5) / W, indexing="ij")
+    z = 1.0 + 4.0 * torch.rand(H, W, generator=g)
+    z[torch.rand(H, W, generator=g) < 0.02] *= -1.0                   # a few points behind the camera
+    x = (u - K[0, 2]) / K[0, 0] * z
+    y = (v - K[1, 2]) / K[1, 1] * z
+    pts = torch.stack([x, y, z], -1).reshape(-1, 3).float()
+    pts[: W] = pts[W: 2 * W]                                          # exact depth ties on shared pixels
+    colors = torch.randint(0, 256, (H * W, 3), generator=g).float()
+    c, s_ = math.cos(tilt), math.sin(tilt)
+    ext = torch.tensor([[c, 0, s_, 0.3 * tilt], [0, 1, 0, -0.1 * tilt], [-s_, 0, c, 0.2 * tilt], [0, 0, 0, 1]],
+                       dtype=torch.float32)
+    return pts, colors, ext, K
+

@@ -130,6 +130,46 @@ def model3d_case(t3d, name, cfg: DiTConfig, grid, batch, seed):
     print(name, tuple(y.shape), float(y.abs().mean()))
 
 
+def project_case():
+    """Outputs of the REAL `render_with_project` (scripts/inference/infer.py:222-258): its source
+    and MoRe4D/utils/project_utils.py are exec'd in place (infer.py itself imports packages that
+    are absent here); `scatter` (torch_scatter, absent) is stubbed with an index_add mean."""
+    import ast
+    import importlib.util
+    import numpy as np
+    ref = os.path.dirname(os.path.dirname(ref_import._PKG)) if False else os.path.dirname(ref_import._PKG)
+    spec = importlib.util.spec_from_file_location("m4d_ref_project_utils",
+                                                  os.path.join(ref_import._PKG, "utils", "project_utils.py"))
+    pu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pu)
+    src = open(os.path.join(ref, "scripts", "inference", "infer.py")).read()
+    tree = ast.parse(src)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "render_with_project"][0]
+
+    def scatter(srcv, index, dim=0, reduce="mean"):
+        assert dim == 0 and reduce == "mean"
+        n = int(index.max()) + 1
+        out = torch.zeros(n, srcv.shape[1], dtype=srcv.dtype)
+        cnt = torch.zeros(n, dtype=srcv.dtype)
+        out.index_add_(0, index, srcv)
+        cnt.index_add_(0, index, torch.ones_like(index, dtype=srcv.dtype))
+        return out / cnt.clamp_min(1)[:, None]
+
+    from typing import Tuple
+    ns = {"torch": torch, "np": np, "project": pu.project, "scatter": scatter, "Tuple": Tuple}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "infer.py:render_with_project", "exec"), ns)
+    render = ns["render_with_project"]
+    out = {}
+    for name, (H, W, seed, tilt) in {"a": (48, 64, 0, 0.0), "b": (37, 53, 1, 0.15)}.items():
+        pts, col, ext, K = synth.point_cloud(H, W, seed, tilt)
+        img, mask = render(pts, ext, K, col, H, W, torch.device("cpu"))
+        out[f"{name}.image"] = torch.from_numpy(np.ascontiguousarray(img))
+        out[f"{name}.mask"] = torch.from_numpy(np.ascontiguousarray(mask.astype(np.uint8)))
+        out[f"{name}.pts_sum"] = checksum(pts)
+        print("project", name, img.shape, float(mask.mean()))
+    save_file(out, os.path.join(OUT, "project.safetensors"))
+
+
 def vae_cases(vae_mod, traj_mod):
     """Real AutoencoderKLWan (chunked encode/decode with the feature cache) and the two
     trajectory adaptors on small clips: 13 frames = 1 + three 4-frame chunks on the encoder
@@ -169,6 +209,9 @@ def main():
     from more4d_b200.config import WAN_TINY_INP
     model3d_case(ref_import.load3d(), "dit3d_tiny", WAN_TINY_INP, (3, 4, 6), 2, seed=5)
     if "--only-3d" in sys.argv:
+        return
+    project_case()
+    if "--only-new" in sys.argv:
         return
     vae_cases(_vae, _traj)
     ops_case(t4d)
