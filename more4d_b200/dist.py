@@ -8,6 +8,11 @@ inside a step.  Two modes:
   * ``sample`` sharding (default): rank r owns samples r, r+P, r+2P, ...; weights replicated;
     ONE all-gather of the final latents after the loop (6 MB/sample at 720p) — the collective
     the north-star names.  Weak scaling, linear by construction.
+  * ``sequence`` (Ulysses) sharding for ONE sample's latency (`SequenceParallel`, the slot of the
+    reference's `enable_multi_gpus_inference` / `usp_attn_forward`, wan_transformer4d.py:1038-1044,
+    1187-1198,1320-1321): every rank holds L/P tokens through all token-local ops (LayerNorm,
+    AdaLN, Linear, cross-attention, FFN); around self-attention one all-to-all trades the token
+    shard of all heads for all tokens of heads/P heads, and one trades it back.
   * ``cfg`` sharding for a single sample on 2 ranks: rank 0 evaluates the unconditional branch,
     rank 1 the text branch of every step; one all-gather of the two noise predictions
     (2 x 6 MB) per step feeds the CFG combine (pipeline_wan_fun_control.py:820-822) on both.
@@ -93,3 +98,55 @@ def cfg_split_noise(noise_fn: Callable[[int], Tensor], group=None):
     both = [torch.empty_like(mine) for _ in range(2)]
     dist.all_gather(both, mine.contiguous(), group=group)
     return both[0], both[1]
+
+
+class SequenceParallel:
+    """Ulysses sequence parallelism over `group` (NCCL on the NVSwitch domain; gloo in tests).
+
+    Layout contract: token shards are contiguous chunks of the (padded) sequence — rank r holds
+    tokens [r*L/P, (r+1)*L/P), like `torch.chunk(x, P, dim=1)[r]` at wan_transformer4d.py:1188 —
+    and head shards are contiguous groups of heads/P heads."""
+
+    def __init__(self, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("SequenceParallel needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def shard_tokens(self, x: Tensor) -> Tensor:
+        """[B, L, ...] -> this rank's [B, L/P, ...] (L % P == 0)."""
+        L = x.shape[1]
+        if L % self.world:
+            raise ValueError(f"sequence length {L} is not a multiple of the SP world size {self.world}")
+        n = L // self.world
+        return x[:, self.rank * n:(self.rank + 1) * n].contiguous()
+
+    def seq_to_heads(self, x: Tensor) -> Tensor:
+        """[S, B, L/P, H, D] (token shard, all heads; S stacked tensors, e.g. q/k/v) ->
+        [S, B, L, H/P, D] (all tokens, this rank's heads).  One all-to-all."""
+        S, B, n, H, D = x.shape
+        P = self.world
+        if H % P:
+            raise ValueError(f"{H} heads cannot be split over {P} ranks")
+        send = x.view(S, B, n, P, H // P, D).permute(3, 0, 1, 2, 4, 5).contiguous()    # [P(dst), S, B, n, H/P, D]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)                           # [P(src), ...]
+        return recv.permute(1, 2, 0, 3, 4, 5).reshape(S, B, P * n, H // P, D)
+
+    def heads_to_seq(self, x: Tensor) -> Tensor:
+        """[B, L, H/P, D] (all tokens, this rank's heads) -> [B, L/P, H, D].  One all-to-all."""
+        B, L, h, D = x.shape
+        P = self.world
+        n = L // P
+        send = x.view(B, P, n, h, D).permute(1, 0, 2, 3, 4).contiguous()               # [P(dst), B, n, h, D]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)                           # [P(src = head group), ...]
+        return recv.permute(1, 2, 0, 3, 4).reshape(B, n, P * h, D)
+
+    def gather_tokens(self, x: Tensor) -> Tensor:
+        """[B, L/P, ...] -> [B, L, ...] on every rank (wan_transformer4d.py:1320-1321)."""
+        parts = [torch.empty_like(x) for _ in range(self.world)]
+        dist.all_gather(parts, x.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+

@@ -159,9 +159,34 @@ class WanSelfAttention(nn.Module):
         self.norm_q = WanRMSNorm(dim, eps, device=device) if qk_norm else None
         self.norm_k = WanRMSNorm(dim, eps, device=device) if qk_norm else None
 
+    def attend_sp(self, x: Tensor, k_lens: Optional[Tensor], grid_i32: Tensor, cos: Tensor, sin: Tensor,
+                  sp) -> Tensor:
+        """Ulysses form of `attend` (the slot of the reference's usp_attn_forward, t4d:1042-1044):
+        x is this rank's token shard [B, L/P, C].  q/k/v projections and the full-channel RMSNorm
+        are token-local; ONE all-to-all hands every rank all L tokens of heads/P heads, where RoPE
+        (needs global token positions) and attention run; one all-to-all brings the output back."""
+        B, n_loc, C = x.shape
+        n, d = self.num_heads, self.head_dim
+        qkv = torch.empty(3, B, n_loc, C, device=x.device, dtype=BF16)
+        for i, lin in enumerate((self.q, self.k, self.v)):
+            ops.linear(x, lin.weight, lin.bias, out=qkv[i])
+        if self.qk_norm:
+            ops.rmsnorm_rope_(qkv[0], self.norm_q.weight, n, self.eps)
+            ops.rmsnorm_rope_(qkv[1], self.norm_k.weight, n, self.eps)
+        full = sp.seq_to_heads(qkv.view(3, B, n_loc, n, d))                 # [3, B, L, n/P, d]
+        h = n // sp.world
+        L = full.shape[2]
+        q, k, v = (full[i].reshape(B, L, h * d) for i in range(3))
+        ops.rmsnorm_rope_(q, None, h, self.eps, cos, sin, grid_i32)
+        ops.rmsnorm_rope_(k, None, h, self.eps, cos, sin, grid_i32)
+        o = ops.attention(q.view(B, L, h, d), k.view(B, L, h, d), v.view(B, L, h, d), k_lens)
+        return sp.heads_to_seq(o).reshape(B, n_loc, C)
+
     def attend(self, x: Tensor, k_lens: Optional[Tensor], grid_i32: Tensor, cos: Tensor,
-               sin: Tensor) -> Tensor:
+               sin: Tensor, sp=None) -> Tensor:
         """x bf16 [B, L, C] -> attention output before the `o` projection, bf16 [B, L, C]."""
+        if sp is not None and sp.world > 1:
+            return self.attend_sp(x, k_lens, grid_i32, cos, sin, sp)
         B, L, C = x.shape
         n, d = self.num_heads, self.head_dim
         q = ops.linear(x, self.q.weight, self.q.bias)
@@ -275,7 +300,7 @@ class WanAttentionBlock(nn.Module):
             self.spatial_guidance_self = self.spatial_guidance_ffn = None
 
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens=None, dtype=BF16,
-                t=0, dino_features=None, use_cls_token=False, cross_kv=None):
+                t=0, dino_features=None, use_cls_token=False, cross_kv=None, sp=None):
         """x: [B, L, C] fp32 (bf16 accepted and widened); e: [B, 6, C] fp32.  Returns the fp32
         residual stream.  A contiguous fp32 `x` is updated in place and returned."""
         _no_grad_only("WanAttentionBlock")
@@ -310,7 +335,7 @@ class WanAttentionBlock(nn.Module):
 
         # self-attention, x += y * e2
         t1 = adaln(0, 1, self.spatial_guidance_self)
-        o = self.self_attn.attend(t1, k_lens, grid, cos, sin)
+        o = self.self_attn.attend(t1, k_lens, grid, cos, sin, sp)
         ops.linear(o, self.self_attn.o.weight, self.self_attn.o.bias, ops.EPI_GATE_RESIDUAL_F32,
                    out=x, residual=x, gate=em[:, 2], gate_batch_stride=ms, rows_per_batch=L)
         # cross-attention, x += y
@@ -442,6 +467,7 @@ class WanTransformer4DModel(nn.Module):
         self.current_steps = 0
         self.num_inference_steps = None
         self.sp_world_size, self.sp_world_rank = 1, 0
+        self.sp = None                # dist.SequenceParallel after enable_multi_gpus_inference()
 
     @classmethod
     def from_config(cls, cfg: DiTConfig, device=None) -> "WanTransformer4DModel":
@@ -458,6 +484,18 @@ class WanTransformer4DModel(nn.Module):
         return self.patch_embedding.weight.dtype
 
     # cfg_skip bookkeeping of the reference (t4d:986-1008, cfg_optimization.py:5-39)
+    def enable_multi_gpus_inference(self, group=None):
+        """t4d:1038-1044: shard ONE sample's sequence over the ranks of `group` (Ulysses).  Needs an
+        initialised torch.distributed process group; num_heads must be a multiple of its size."""
+        from .dist import SequenceParallel
+        sp = SequenceParallel(group)
+        if self.num_heads % sp.world:
+            raise ValueError(f"{self.num_heads} heads cannot be split over {sp.world} ranks")
+        self.sp, self.sp_world_size, self.sp_world_rank = sp, sp.world, sp.rank
+
+    def disable_multi_gpus_inference(self):
+        self.sp, self.sp_world_size, self.sp_world_rank = None, 1, 0
+
     def enable_cfg_skip(self, cfg_skip_ratio, num_steps):
         if cfg_skip_ratio != 0:
             self.cfg_skip_ratio, self.current_steps, self.num_inference_steps = cfg_skip_ratio, 0, num_steps
@@ -592,6 +630,11 @@ class WanTransformer4DModel(nn.Module):
             ctx = self.embed_context([c.to(device=dev, dtype=BF16) for c in context], clip_fea)
         seq_lens = torch.full((B,), n_tok, device=dev, dtype=torch.int32)
         grid_sizes = torch.tensor([grid] * B, device=dev, dtype=torch.int32)
+        sp = self.sp if self.sp_world_size > 1 else None
+        if sp is not None:                                         # context parallel, t4d:1187-1198
+            if guidance_features is not None:
+                raise NotImplementedError("Motion-Perception guidance under sequence parallelism")
+            xs = sp.shard_tokens(xs)
         run_blocks = True
         tc = self.teacache
         if tc is not None:                                         # t4d:1200-1270
@@ -605,7 +648,7 @@ class WanTransformer4DModel(nn.Module):
             for i, blk in enumerate(self.blocks):
                 xs = blk(xs, e0, seq_lens, grid_sizes, self.freqs, ctx, None, BF16, t,
                          dino_features=guidance_features, use_cls_token=self.use_cls_token,
-                         cross_kv=None if conditioning is None else conditioning.cross_kv[i])
+                         cross_kv=None if conditioning is None else conditioning.cross_kv[i], sp=sp)
             if tc is not None:
                 res = (xs.cpu() - ori) if tc.offload else (xs - ori)
                 if cond_flag:
@@ -613,6 +656,8 @@ class WanTransformer4DModel(nn.Module):
                 else:
                     tc.previous_residual_uncond = res
         tok = self.head(xs, e)                                     # [B, L, 64] bf16
+        if sp is not None:
+            tok = sp.gather_tokens(tok)                            # t4d:1320-1321
         out = ops.unpatchify(tok, ref_len, self.out_dim, T, H, W)
         if tc is not None:
             tc.step_done(cond_flag)

@@ -67,3 +67,43 @@ def test_sample_sharding_matches_single_rank():
                 assert torch.equal(torch.from_numpy(a), b.float())
             assert torch.equal(torch.from_numpy(u), torch.full((2, 3), 1.0))
             assert torch.equal(torch.from_numpy(t), torch.full((2, 3), 2.0))
+
+
+def _sp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sp = mdist.SequenceParallel()
+        g = torch.Generator().manual_seed(0)
+        S, B, L, H, D = 3, 2, 12, 4, 5
+        full = torch.randn(S, B, L, H, D, generator=g)                     # identical on every rank
+        n = L // world
+        mine = full[:, :, rank * n:(rank + 1) * n].contiguous()            # token shard, all heads
+        heads = sp.seq_to_heads(mine)                                      # all tokens, my heads
+        h = H // world
+        ok1 = torch.equal(heads, full[:, :, :, rank * h:(rank + 1) * h])
+        back = sp.heads_to_seq(heads[0])                                   # [B, n, H, D]
+        ok2 = torch.equal(back, mine[0])
+        tok = sp.shard_tokens(full[0].reshape(B, L, H * D))
+        ok3 = torch.equal(tok, mine[0].reshape(B, n, H * D))
+        ok4 = torch.equal(sp.gather_tokens(tok), full[0].reshape(B, L, H * D))
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3), bool(ok4)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sequence_parallel_layout_roundtrip():
+    """Ulysses all-to-alls (world 2, gloo): token shard x all heads -> all tokens x head shard is
+    exactly the corresponding slice of the full tensor, and the inverse restores the shard."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1:] == (True, True, True, True), r
