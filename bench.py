@@ -120,6 +120,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug only: truncate the block stack (number is then INVALID)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="sample", choices=["sample", "sp"],
+                    help="sample: one sample per GPU (weak scaling, the default / headline); sp: ONE sample, "
+                         "sequence sharded over the GPUs (Ulysses all-to-alls; strong scaling, single-sample latency)")
     ap.add_argument("--hoist-conditioning", action="store_true",
                     help="compute the step-invariant context embedding / cross-attention K/V once instead of "
                          "per step (bit-identical; NOT the default: the reference recomputes them every step)")
@@ -141,7 +144,9 @@ def main():
     config = {"workload": f"{args.workload}: Wan2.1-14B-{'InP' if visim else 'Control'} dims (C{cfg.dim} F{cfg.ffn_dim} "
                           f"{cfg.num_heads}h x{cfg.num_layers}L) {frames}x{height}x{width}, "
                           f"L={L} tokens, CFG batch 2, 1 sample/GPU",
-              "parallelism": f"dp{world} (sample-sharded replicas, all-gather of final latents)",
+              "parallelism": (f"sp{world} (one sample, Ulysses sequence sharding: 2 all-to-alls per block)"
+                              if args.parallelism == "sp" and world > 1 else
+                              f"dp{world} (sample-sharded replicas, all-gather of final latents)"),
               "l2": "inputs (28 GB weights + GB-scale activations) exceed the 126 MB L2 every step",
               "layers_override": args.layers or None,
               "hoist_conditioning": bool(args.hoist_conditioning)}
@@ -184,14 +189,18 @@ def main():
     den = (ViSMDenoiser if visim else StraGDenoiser)(model, guidance_scale=6.0, shift=5.0,
                                                      num_inference_steps=50,
                                                      hoist_conditioning=args.hoist_conditioning)
+    sp_mode = args.parallelism == "sp" and world > 1
+    if sp_mode:
+        model.enable_multi_gpus_inference()
+    data_seed = 0 if sp_mode else rank                       # sp: every rank works on the SAME sample
     lat_t = (frames - 1) // 4 + 1
     latent_shape = (1, 16, lat_t, height // 8, width // 8)
     if visim:
-        lat_host, cond_host = synthetic_visim_conditioning(latent_shape, seed=rank, device="cpu",
+        lat_host, cond_host = synthetic_visim_conditioning(latent_shape, seed=data_seed, device="cpu",
                                                            text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
         lat_host = lat_host.pin_memory()
     else:
-        lat_host, cond_host = synthetic_conditioning(latent_shape, seed=rank, device="cpu", pin=True,
+        lat_host, cond_host = synthetic_conditioning(latent_shape, seed=data_seed, device="cpu", pin=True,
                                                      text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
     lat = lat_host.to(dev)
     cond = cond_host.to(dev)
@@ -219,7 +228,7 @@ def main():
     torch.cuda.nvtx.range_push("m4d_timed")          # ncu --nvtx --nvtx-include "m4d_timed/"
     ev0.record()
     run(args.steps, lat, args.warmup)
-    if world > 1:
+    if world > 1 and not sp_mode:
         gathered = mdist.gather_latents([lat], world)     # the north-star's one collective
     ev1.record()
     barrier()
@@ -231,7 +240,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    value = world * args.steps / (ms_total / 1000.0)
+    units = 1 if sp_mode else world                          # samples advanced per step by the whole job
+    value = units * args.steps / (ms_total / 1000.0)
 
     # ---- end to end through the public API with HOST buffers (pinned H2D in, D2H out, every step)
     h2d = lat_host.numel() * 2 + cond_host.nbytes()
@@ -245,7 +255,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / float(e2e_s.item())
+    e2e_value = units * args.steps / float(e2e_s.item())
 
     if rank != 0:
         if world > 1:
@@ -276,7 +286,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong" if sp_mode else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "dit_forwards_per_s": value * 2,
