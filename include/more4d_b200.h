@@ -97,6 +97,16 @@ int m4d_rmsnorm_rope(void* x, long long row_stride, const void* weight, const fl
                      const float* rope_sin, const int* grid_fhw, int B, int L, int heads,
                      int head_dim, float eps, void* stream);
 
+/* WanRMSNorm over the full channel dim (wan_transformer4d.py:378-394; weight NULL = plain copy)
+ * whose output is scattered by head group: dst[g] (HOST array of P <= 8 DEVICE pointers, possibly
+ * peer-GPU memory) receives channels [g*C/P, (g+1)*C/P) of local token (b, l) at element
+ * b*dst_batch_stride + (dst_row0 + l)*(C/P).  The sending half of the sequence-parallel
+ * (Ulysses) exchange around self-attention — the slot of the reference's usp_attn_forward,
+ * wan_transformer4d.py:1038-1044 — fused into the normalisation pass over NVLink P2P stores. */
+int m4d_rmsnorm_scatter(const void* x, long long row_stride, const void* weight, int B, int L_local,
+                        int C, float eps, void* const* dst, int P, long long dst_batch_stride,
+                        long long dst_row0, void* stream);
+
 /* y[M,N] fp32 = [SiLU](x[M,K] fp32) . w[N,K]^T(bf16) + bias, optional SiLU on y; M <= 8.
  * The time-embedding MLPs, which the reference runs in fp32 (wan_transformer4d.py:1160-1171). */
 int m4d_small_linear_f32(const float* x, const void* w, const void* bias, float* y, int M, int N,

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "m4d_layernorm_modulate": (c_int, [_P, _I, _P, _P, _P, _P, _L, _L, _I, _I, _F, _P, _I, _P, _L,
                                        _I, _P, _P]),
     "m4d_rmsnorm_rope": (c_int, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "m4d_rmsnorm_scatter": (c_int, [_P, _L, _P, _I, _I, _I, _F, _P, _I, _L, _L, _P]),
     "m4d_small_linear_f32": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "m4d_timestep_embedding": (c_int, [_P, _I, _I, _P, _P]),
     "m4d_add_bcast_f32": (c_int, [_P, _P, _P, _I, _L, _L, _P]),

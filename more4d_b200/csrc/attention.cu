@@ -380,8 +380,11 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float m_new = fmaxf(m_used, mx);
         const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, grow)) {
-          const float f = fast_exp2((m_used - m_new) * c);
-          m_used = m_new;
+          // only rows that crossed the threshold THEMSELVES move their reference max: a row's
+          // result then depends on its own logits alone, not on which 31 rows share its warp,
+          // so chunking the queries differently (sequence-parallel launches) is bit-identical
+          const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;
+          if (grow) m_used = m_new;
           l_sum *= f;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -695,8 +698,8 @@ attn_fwd_d128_k64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(&pv_done[t], (j - 1) & 1);       // PV_t(j-1) must have landed in O_t
           tc_fence_after();
-          const float f = fast_exp2((m_used - m_new) * c);
-          m_used = m_new;
+          const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;   // per-row, see the main kernel
+          if (grow) m_used = m_new;
           l_sum *= f;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -1010,8 +1013,8 @@ attn_fwd_d128_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const float m_new = fmaxf(m_used, mx);
         const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, grow)) {              // identical in the partner warp
-          const float f = fast_exp2((m_used - m_new) * c);
-          m_used = m_new;
+          const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;   // per-row, see the main kernel
+          if (grow) m_used = m_new;
           l_sum *= f;
 #pragma unroll 1
           for (int cc = 0; cc < 2; ++cc) {                 // this half's 64 columns of O

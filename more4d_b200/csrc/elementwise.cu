@@ -408,6 +408,85 @@ extern "C" int m4d_layernorm_modulate(const void* x, int x_is_bf16, const void* 
   return M4D_OK;
 }
 
+namespace m4d {
+
+// WanRMSNorm over the full channel dim (wan_transformer4d.py:378-394) whose output is SCATTERED
+// by head group into P destination buffers — the sending half of the Ulysses all-to-all of the
+// sequence-parallel self-attention, fused into the normalisation pass: destination g receives
+// channels [g*C/P, (g+1)*C/P) of every local token at row dst_row0 + l of its [B, L, C/P]
+// buffer.  The destinations are peer GPUs' memory (NVLink P2P stores through symmetric-memory
+// mappings), so the exchange costs no pass of its own.  Same arithmetic as rmsnorm_rope_kernel.
+struct ScatterDst {
+  bf16* ptr[8];
+};
+
+__global__ void __launch_bounds__(ROW_THREADS)
+rmsnorm_scatter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ weight, ScatterDst dst,
+                       int L_local, int C, int group_c, float eps, long long row_stride,
+                       long long dst_batch_stride, long long dst_row0) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const int b = static_cast<int>(row / L_local);
+  const int l = static_cast<int>(row - static_cast<long long>(b) * L_local);
+  const bf16* xr = x + row * row_stride;
+  const int nvec = C >> 2;
+  float4 v[ROW_MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i) {
+    const int vi = threadIdx.x + i * ROW_THREADS;
+    if (vi < nvec) {
+      v[i] = load4(xr + vi * 4);
+      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  float rstd = 1.f;
+  if (weight != nullptr) rstd = bf16_round(rsqrtf(block_sum(ss, red) / C + eps));
+  const long long drow = static_cast<long long>(b) * dst_batch_stride + (dst_row0 + l) * group_c;
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i) {
+    const int vi = threadIdx.x + i * ROW_THREADS;
+    if (vi < nvec) {
+      const int c0 = vi * 4;
+      float4 y = v[i];
+      if (weight != nullptr) {
+        const float4 w = load4(weight + c0);
+        y.x = bf16_round(bf16_round(y.x * rstd) * w.x);
+        y.y = bf16_round(bf16_round(y.y * rstd) * w.y);
+        y.z = bf16_round(bf16_round(y.z * rstd) * w.z);
+        y.w = bf16_round(bf16_round(y.w * rstd) * w.w);
+      }
+      const int g = c0 / group_c;                  // group_c % 4 == 0: a vector never straddles groups
+      store4(dst.ptr[g] + drow + (c0 - g * group_c), y);
+    }
+  }
+}
+
+}  // namespace m4d
+
+extern "C" int m4d_rmsnorm_scatter(const void* x, long long row_stride, const void* weight, int B,
+                                   int L_local, int C, float eps, void* const* dst, int P,
+                                   long long dst_batch_stride, long long dst_row0, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && dst && B > 0 && L_local > 0 && C > 0 && P >= 1 && P <= 8, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(C % (4 * P) == 0 && C <= ROW_THREADS * 4 * ROW_MAXV, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(row_stride >= C && row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+              M4D_ERR_ALIGN);
+  ScatterDst d;
+  for (int g = 0; g < 8; ++g) {
+    d.ptr[g] = g < P ? static_cast<bf16*>(dst[g]) : nullptr;
+    M4D_REQUIRE(g >= P || (d.ptr[g] != nullptr && (reinterpret_cast<uintptr_t>(d.ptr[g]) & 7) == 0),
+                M4D_ERR_ALIGN);
+  }
+  const long long rows = static_cast<long long>(B) * L_local;
+  M4D_REQUIRE(rows < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  rmsnorm_scatter_kernel<<<static_cast<unsigned>(rows), ROW_THREADS, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<const bf16*>(weight), d, L_local, C, C / P, eps, row_stride,
+      dst_batch_stride, dst_row0);
+  M4D_CHECK_LAUNCH("rmsnorm_scatter_kernel");
+  return M4D_OK;
+}
+
 extern "C" int m4d_rmsnorm_rope(void* x, long long row_stride, const void* weight,
                                 const float* rope_cos, const float* rope_sin, const int* grid_fhw,
                                 int B, int L, int heads, int head_dim, float eps, void* stream_) {

@@ -19,6 +19,7 @@ inside a step.  Two modes:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -107,12 +108,21 @@ class SequenceParallel:
     tokens [r*L/P, (r+1)*L/P), like `torch.chunk(x, P, dim=1)[r]` at wan_transformer4d.py:1188 —
     and head shards are contiguous groups of heads/P heads."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, peer_memory: bool = True):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("SequenceParallel needs an initialised torch.distributed process group")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        # fused exchange over symmetric (peer-mapped) memory; False = NCCL all-to-alls + permutes
+        self.peer_memory = peer_memory
+        self._peer = {}
+
+    def peer_buffers(self, B: int, L: int, C: int, device) -> "PeerBuffers":
+        key = (B, L, C, str(device))
+        if key not in self._peer:
+            self._peer[key] = PeerBuffers(self, B, L, C, device)       # collective: same order on all ranks
+        return self._peer[key]
 
     def shard_tokens(self, x: Tensor) -> Tensor:
         """[B, L, ...] -> this rank's [B, L/P, ...] (L % P == 0)."""
@@ -149,4 +159,31 @@ class SequenceParallel:
         parts = [torch.empty_like(x) for _ in range(self.world)]
         dist.all_gather(parts, x.contiguous(), group=self.group)
         return torch.cat(parts, dim=1)
+
+
+class PeerBuffers:
+    """Receive buffers of the FUSED sequence-parallel exchange, allocated in torch symmetric memory so
+    that every rank holds P2P (NVLink) mappings of all peers' buffers: producers — the v-projection
+    GEMM epilogue, the q/k RMSNorm kernel, the attention epilogue — store straight into the
+    consumer's buffer in its final layout; what remains of the all-to-all is a barrier.
+
+        qkv [3, B, L, C/P]   all tokens, this rank's heads   (written by every rank's projections)
+        o   [B, L/P, C]      this rank's tokens, all heads   (written by every rank's attention)
+    """
+
+    def __init__(self, sp: "SequenceParallel", B: int, L: int, C: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        P = sp.world
+        self.shape = (B, L, C)
+        group = sp.group if sp.group is not None else dist.group.WORLD
+        self.qkv = symm_mem.empty(3, B, L, C // P, dtype=torch.bfloat16, device=device)
+        self.o = symm_mem.empty(B, L // P, C, dtype=torch.bfloat16, device=device)
+        self._h_qkv = symm_mem.rendezvous(self.qkv, group)
+        self._h_o = symm_mem.rendezvous(self.o, group)
+        self.qkv_peers = [self._h_qkv.get_buffer(g, (3, B, L, C // P), torch.bfloat16) for g in range(P)]
+        self.o_peers = [self._h_o.get_buffer(g, (B, L // P, C), torch.bfloat16) for g in range(P)]
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier over the group's signal pads (a ~7 us kernel)."""
+        self._h_qkv.barrier()
 

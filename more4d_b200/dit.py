@@ -167,6 +167,8 @@ class WanSelfAttention(nn.Module):
         (needs global token positions) and attention run; one all-to-all brings the output back."""
         B, n_loc, C = x.shape
         n, d = self.num_heads, self.head_dim
+        if sp.peer_memory and x.is_cuda:
+            return self._attend_sp_peer(x, k_lens, grid_i32, cos, sin, sp)
         qkv = torch.empty(3, B, n_loc, C, device=x.device, dtype=BF16)
         for i, lin in enumerate((self.q, self.k, self.v)):
             ops.linear(x, lin.weight, lin.bias, out=qkv[i])
@@ -181,6 +183,44 @@ class WanSelfAttention(nn.Module):
         ops.rmsnorm_rope_(k, None, h, self.eps, cos, sin, grid_i32)
         o = ops.attention(q.view(B, L, h, d), k.view(B, L, h, d), v.view(B, L, h, d), k_lens)
         return sp.heads_to_seq(o).reshape(B, n_loc, C)
+
+    def _attend_sp_peer(self, x: Tensor, k_lens: Optional[Tensor], grid_i32: Tensor, cos: Tensor,
+                        sin: Tensor, sp) -> Tensor:
+        """The same exchange with NO pass of its own: producers store straight into the consumer
+        rank's buffer over NVLink (dist.PeerBuffers) —
+          v        : the projection GEMM's epilogue writes head group g into rank g's buffer,
+          q, k     : the RMSNorm kernel (full-channel statistics need the whole local row, so the
+                     GEMM stays local) scatters its output by head group (m4d_rmsnorm_scatter),
+          attention: one launch per destination rank writes that rank's token chunk into its `o`
+                     buffer at this rank's head columns —
+        and each all-to-all shrinks to a ~7 us barrier.  Bit-identical to the unsharded forward."""
+        B, n_loc, C = x.shape
+        n, d, P, r = self.num_heads, self.head_dim, sp.world, sp.rank
+        h, gc = n // P, C // P
+        L = n_loc * P
+        pb = sp.peer_buffers(B, L, C, x.device)
+        rows = slice(r * n_loc, (r + 1) * n_loc)
+        for g in range(P):
+            wv, bv = self.v.weight[g * gc:(g + 1) * gc], self.v.bias[g * gc:(g + 1) * gc]
+            for b in range(B):
+                ops.linear(x[b], wv, bv, out=pb.qkv_peers[g][2, b, rows])
+        q = ops.linear(x, self.q.weight, self.q.bias)
+        k = ops.linear(x, self.k.weight, self.k.bias)
+        ops.rmsnorm_scatter(q, self.norm_q.weight if self.qk_norm else None, [p_[0] for p_ in pb.qkv_peers],
+                            r * n_loc, self.eps)
+        ops.rmsnorm_scatter(k, self.norm_k.weight if self.qk_norm else None, [p_[1] for p_ in pb.qkv_peers],
+                            r * n_loc, self.eps)
+        pb.barrier()                                   # every rank's pieces have landed in pb.qkv
+        qf, kf, vf = pb.qkv[0], pb.qkv[1], pb.qkv[2]   # [B, L, h*d]: all tokens, my heads
+        ops.rmsnorm_rope_(qf, None, h, self.eps, cos, sin, grid_i32)
+        ops.rmsnorm_rope_(kf, None, h, self.eps, cos, sin, grid_i32)
+        k4, v4 = kf.view(B, L, h, d), vf.view(B, L, h, d)
+        for s_ in range(P):                            # token chunk s_ belongs to rank s_
+            q4 = qf[:, s_ * n_loc:(s_ + 1) * n_loc].view(B, n_loc, h, d)
+            out = pb.o_peers[s_].view(B, n_loc, n, d)[:, :, r * h:(r + 1) * h]
+            ops.attention(q4, k4, v4, k_lens, out=out)
+        pb.barrier()                                   # every rank's head columns have landed in pb.o
+        return pb.o
 
     def attend(self, x: Tensor, k_lens: Optional[Tensor], grid_i32: Tensor, cos: Tensor,
                sin: Tensor, sp=None) -> Tensor:

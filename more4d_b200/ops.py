@@ -188,6 +188,26 @@ def rmsnorm_rope_(x: Tensor, weight: Optional[Tensor], heads: int, eps: float = 
     return x
 
 
+def rmsnorm_scatter(x: Tensor, weight: Optional[Tensor], dst, dst_row0: int, eps: float = 1e-6) -> None:
+    """WanRMSNorm of x [B, L_local, C] bf16, scattered by head group: dst[g] ([B, L, C/P] bf16, this
+    or a peer GPU's memory) receives channels [g*C/P, (g+1)*C/P) at rows dst_row0 + l."""
+    import ctypes
+    _lib.require_device()
+    _req(x, BF16, "x")
+    B, Ll, C = x.shape
+    P = len(dst)
+    if x.stride(2) != 1 or x.stride(0) != Ll * x.stride(1):
+        raise ValueError("more4d_b200.rmsnorm_scatter: x rows must be uniformly strided")
+    for d in dst:
+        _req(d, BF16, "dst")
+        if d.dim() != 3 or d.shape[0] != B or d.shape[2] != C // P or not d.is_contiguous():
+            raise ValueError("more4d_b200.rmsnorm_scatter: dst[g] must be contiguous [B, L, C/P]")
+    ptrs = (ctypes.c_void_p * P)(*[d.data_ptr() for d in dst])
+    rc = _lib.lib().m4d_rmsnorm_scatter(x.data_ptr(), x.stride(1), _ptr(weight), B, Ll, C, eps, ptrs, P,
+                                        dst[0].stride(0), dst_row0, _stream())
+    _lib.check(rc, "m4d_rmsnorm_scatter")
+
+
 def small_linear_f32(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu_in: bool = False,
                      silu_out: bool = False) -> Tensor:
     _lib.require_device()

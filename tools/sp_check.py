@@ -35,11 +35,14 @@ def main():
               seq_len=inp["seq_len"], clip_fea=inp["clip_fea"].to(dev), y=inp["y"].to(dev),
               full_ref=inp["full_ref"].to(dev))
     y_ref = model(**kw)
-    model.enable_multi_gpus_inference()
-    y_sp = model(**kw)
-    model.disable_multi_gpus_inference()
-    out["parity_bit_exact"] = bool(torch.equal(y_ref, y_sp))
-    out["parity_rel"] = float((y_ref.float() - y_sp.float()).norm() / y_ref.float().norm())
+    for mode, peer in (("nccl", False), ("peer", True)):
+        model.enable_multi_gpus_inference()
+        model.sp.peer_memory = peer
+        y_sp = model(**kw)
+        y_sp2 = model(**kw)                                   # buffers re-used across calls
+        model.disable_multi_gpus_inference()
+        out[f"parity_bit_exact_{mode}"] = bool(torch.equal(y_ref, y_sp) and torch.equal(y_ref, y_sp2))
+        out[f"parity_rel_{mode}"] = float((y_ref.float() - y_sp.float()).norm() / y_ref.float().norm())
     del model
 
     # ---- timing: 720p, 14B dims, `layers` blocks, CFG batch 2: unsharded vs sharded forward
@@ -68,9 +71,15 @@ def main():
 
     t1, y1 = timed()
     model.enable_multi_gpus_inference()
+    model.sp.peer_memory = False
     t2, y2 = timed()
-    out.update(layers=a.layers, ms_forward_unsharded=t1, ms_forward_sp=t2, speedup=t1 / t2,
-               fullsize_bit_exact=bool(torch.equal(y1, y2)))
+    model.sp.peer_memory = True
+    t3, y3 = timed()
+    out.update(layers=a.layers, ms_forward_unsharded=t1, ms_forward_sp_nccl=t2, ms_forward_sp_peer=t3,
+               speedup_nccl=t1 / t2, speedup_peer=t1 / t3,
+               fullsize_bit_exact_nccl=bool(torch.equal(y1, y2)), fullsize_bit_exact_peer=bool(torch.equal(y1, y3)),
+               fullsize_rel_peer=float((y1.float() - y3.float()).norm() / y1.float().norm()),
+               fullsize_mismatch_frac_peer=float((y1 != y3).float().mean()))
     if rank == 0:
         print(json.dumps(out))
     dist.destroy_process_group()
