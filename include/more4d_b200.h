@@ -77,6 +77,18 @@ int m4d_attention_fwd(const void* q, const void* k, const void* v, void* out, in
                       long long out_stride_l, const int* k_lens, float softmax_scale,
                       int accumulate, void* stream);
 
+/* m4d_attention_fwd whose epilogue SCATTERS the query rows over n_out <= 8 output buffers: row l goes
+ * to out[l / rows_per_out] (HOST array of DEVICE pointers, possibly peer-GPU memory) at row
+ * l % rows_per_out, with the given batch / token strides.  The returning half of the
+ * sequence-parallel (Ulysses) exchange — the slot of the reference's usp_attn_forward,
+ * wan_transformer4d.py:1038-1044 — fused into the attention epilogue: every rank's token chunk of
+ * this rank's heads is stored straight into that rank's buffer over NVLink, in ONE launch. */
+int m4d_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* out, int n_out,
+                              int rows_per_out, int B, int Lq, int Lk, int heads, int head_dim,
+                              long long q_stride_b, long long q_stride_l, long long kv_stride_b,
+                              long long kv_stride_l, long long out_stride_b, long long out_stride_l,
+                              const int* k_lens, float softmax_scale, void* stream);
+
 /* out = LayerNorm(x) [* weight + bias] [* (1 + scale[b]) + shift[b]], one pass.
  * Replaces F.layer_norm + modulation at wan_transformer4d.py:662,677 (norm1/norm2 + AdaLN),
  * :674 (norm3, affine), :720 (head), :729,733 (MLPProj).  x fp32 or bf16 [rows, C]; weight,

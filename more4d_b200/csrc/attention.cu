@@ -137,6 +137,11 @@ struct AttnParams {
   float scale_log2;                       // softmax_scale * log2(e)
   int accumulate;                         // out = bf16(out + bf16(o))  (summed cross-attention)
   int flags;                              // debug variants, see m4d_set_debug_flags
+  // scatter epilogue (sequence-parallel exchange fused into the attention epilogue): query row l
+  // is stored to out_scatter[l / scatter_rows] at row l % scatter_rows — the destinations are
+  // the ranks' receive buffers (peer memory), one launch serves all of them
+  bf16* out_scatter[8];
+  int scatter_rows;                       // 0 = plain output
 };
 
 // VAR = 0: P is handed to the tensor pipe in two 64-key halves; VAR = 1: in four 32-key
@@ -439,8 +444,15 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float inv_l = 1.0f / l_sum;
     const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
     const bool row_ok = q_row < p.Lq;
-    bf16* orow = p.out + static_cast<long long>(b) * p.out_stride_b +
-                 static_cast<long long>(q_row) * p.out_stride_l + head * A_D;
+    bf16* obase = p.out;
+    int o_row = q_row;
+    if (p.scatter_rows > 0 && row_ok) {
+      const int dst = q_row / p.scatter_rows;
+      obase = p.out_scatter[dst];
+      o_row = q_row - dst * p.scatter_rows;
+    }
+    bf16* orow = obase + static_cast<long long>(b) * p.out_stride_b +
+                 static_cast<long long>(o_row) * p.out_stride_l + head * A_D;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       uint32_t o[32];
@@ -1092,12 +1104,20 @@ attn_fwd_d128_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 
 using namespace m4d;
 
-extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, void* out, int B,
-                                 int Lq, int Lk, int heads, int head_dim, long long q_stride_b,
-                                 long long q_stride_l, long long kv_stride_b, long long kv_stride_l,
-                                 long long out_stride_b, long long out_stride_l, const int* k_lens,
-                                 float softmax_scale, int accumulate, void* stream_) {
+static int attention_impl(const void* q, const void* k, const void* v, void* out, int B,
+                          int Lq, int Lk, int heads, int head_dim, long long q_stride_b,
+                          long long q_stride_l, long long kv_stride_b, long long kv_stride_l,
+                          long long out_stride_b, long long out_stride_l, const int* k_lens,
+                          float softmax_scale, int accumulate, void* const* out_scatter, int n_scatter,
+                          int scatter_rows, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_scatter > 0) {
+    M4D_REQUIRE(out_scatter && n_scatter <= 8 && scatter_rows > 0 &&
+                    static_cast<long long>(n_scatter) * scatter_rows >= Lq && !accumulate,
+                M4D_ERR_BAD_SHAPE);
+    for (int i = 0; i < n_scatter; ++i) M4D_REQUIRE(out_scatter[i] && aligned16(out_scatter[i]), M4D_ERR_ALIGN);
+    out = out_scatter[0];
+  }
   M4D_REQUIRE(q && k && v && out, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(head_dim == A_D, M4D_ERR_UNSUPPORTED);          // d = 128 is the Wan2.1 invariant
@@ -1174,8 +1194,34 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
                  1.4426950408889634f;
   p.accumulate = accumulate;
   p.flags = g_debug_flags;
+  p.scatter_rows = n_scatter > 0 ? scatter_rows : 0;
+  for (int i = 0; i < 8; ++i) p.out_scatter[i] = i < n_scatter ? static_cast<bf16*>(out_scatter[i]) : nullptr;
+  if (n_scatter > 0 && kern != static_cast<void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams)>(
+                                   attn_fwd_d128_kernel<0, 0, 0>))
+    return M4D_ERR_UNSUPPORTED;                 // the measured debug variants have no scatter epilogue
   dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
   kern<<<grid, threads, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
   M4D_CHECK_LAUNCH("attn_fwd_d128_kernel");
   return M4D_OK;
 }
+
+extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, void* out, int B,
+                                 int Lq, int Lk, int heads, int head_dim, long long q_stride_b,
+                                 long long q_stride_l, long long kv_stride_b, long long kv_stride_l,
+                                 long long out_stride_b, long long out_stride_l, const int* k_lens,
+                                 float softmax_scale, int accumulate, void* stream_) {
+  return attention_impl(q, k, v, out, B, Lq, Lk, heads, head_dim, q_stride_b, q_stride_l, kv_stride_b,
+                        kv_stride_l, out_stride_b, out_stride_l, k_lens, softmax_scale, accumulate, nullptr,
+                        0, 0, stream_);
+}
+
+extern "C" int m4d_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* out, int n_out,
+                                         int rows_per_out, int B, int Lq, int Lk, int heads, int head_dim,
+                                         long long q_stride_b, long long q_stride_l, long long kv_stride_b,
+                                         long long kv_stride_l, long long out_stride_b, long long out_stride_l,
+                                         const int* k_lens, float softmax_scale, void* stream_) {
+  return attention_impl(q, k, v, nullptr, B, Lq, Lk, heads, head_dim, q_stride_b, q_stride_l, kv_stride_b,
+                        kv_stride_l, out_stride_b, out_stride_l, k_lens, softmax_scale, 0, out, n_out,
+                        rows_per_out, stream_);
+}
+

@@ -191,8 +191,9 @@ class WanSelfAttention(nn.Module):
           v        : the projection GEMM's epilogue writes head group g into rank g's buffer,
           q, k     : the RMSNorm kernel (full-channel statistics need the whole local row, so the
                      GEMM stays local) scatters its output by head group (m4d_rmsnorm_scatter),
-          attention: one launch per destination rank writes that rank's token chunk into its `o`
-                     buffer at this rank's head columns —
+          attention: ONE launch whose epilogue routes every query row to the rank that owns its token
+                     chunk, into that rank's `o` buffer at this rank's head columns
+                     (m4d_attention_fwd_scatter) —
         and each all-to-all shrinks to a ~7 us barrier.  Bit-identical to the unsharded forward."""
         B, n_loc, C = x.shape
         n, d, P, r = self.num_heads, self.head_dim, sp.world, sp.rank
@@ -215,10 +216,9 @@ class WanSelfAttention(nn.Module):
         ops.rmsnorm_rope_(qf, None, h, self.eps, cos, sin, grid_i32)
         ops.rmsnorm_rope_(kf, None, h, self.eps, cos, sin, grid_i32)
         k4, v4 = kf.view(B, L, h, d), vf.view(B, L, h, d)
-        for s_ in range(P):                            # token chunk s_ belongs to rank s_
-            q4 = qf[:, s_ * n_loc:(s_ + 1) * n_loc].view(B, n_loc, h, d)
-            out = pb.o_peers[s_].view(B, n_loc, n, d)[:, :, r * h:(r + 1) * h]
-            ops.attention(q4, k4, v4, k_lens, out=out)
+        # ONE launch over all L queries; the epilogue stores token chunk s into rank s's buffer
+        outs = [pb.o_peers[s_].view(B, n_loc, n, d)[:, :, r * h:(r + 1) * h] for s_ in range(P)]
+        ops.attention_scatter(qf.view(B, L, h, d), k4, v4, outs, k_lens)
         pb.barrier()                                   # every rank's head columns have landed in pb.o
         return pb.o
 

@@ -139,6 +139,42 @@ def attention(q: Tensor, k: Tensor, v: Tensor, k_lens: Optional[Tensor] = None,
     return out
 
 
+def attention_scatter(q: Tensor, k: Tensor, v: Tensor, outs, k_lens: Optional[Tensor] = None) -> None:
+    """attention(q, k, v) with query rows scattered over `outs`: rows [i*R, (i+1)*R) go to outs[i]
+    ([B, R, N, 128] views with equal strides — typically peer GPUs' buffers), one launch."""
+    import ctypes
+    _lib.require_device()
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, BF16, n)
+        if t.dim() != 4 or t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+            raise ValueError(f"more4d_b200.attention_scatter: `{n}` must be [B, L, N, D] with contiguous (N, D)")
+    B, Lq, N, D = q.shape
+    Lk = k.shape[1]
+    if k.stride() != v.stride():
+        raise ValueError("more4d_b200.attention_scatter: k and v must share strides")
+    R = outs[0].shape[1]
+    for o in outs:
+        _req(o, BF16, "out")
+        if o.shape != (B, R, N, D) or o.stride() != outs[0].stride() or o.stride(3) != 1 or o.stride(2) != D:
+            raise ValueError("more4d_b200.attention_scatter: outs must be equally strided [B, R, N, D] views")
+    if len(outs) * R < Lq:
+        raise ValueError("more4d_b200.attention_scatter: outs do not cover the query rows")
+    ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    if k_lens is not None:
+        _req(k_lens, torch.int32, "k_lens")
+    timed = _Stats.timed is not None and Lq == Lk
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    rc = _lib.lib().m4d_attention_fwd_scatter(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), ptrs, len(outs), R, B, Lq, Lk, N, D, q.stride(0), q.stride(1),
+        k.stride(0), k.stride(1), outs[0].stride(0), outs[0].stride(1), _ptr(k_lens), 0.0, _stream())
+    _lib.check(rc, "m4d_attention_fwd_scatter")
+    if timed:
+        ev1.record()
+        _Stats.timed["attention"].append((ev0, ev1, 4.0 * B * N * Lq * Lk * D))
+
+
 def layernorm_modulate(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
                        shift: Optional[Tensor] = None, scale: Optional[Tensor] = None,
                        mod_batch_stride: int = 0, rows_per_batch: Optional[int] = None,

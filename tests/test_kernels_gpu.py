@@ -240,3 +240,34 @@ def test_cfg_euler_step(ops):
     ref = (lat.float() + dt * npred.float()).to(BF16)
     out = ops.cfg_euler_step_(lat.cuda().clone(), u.cuda(), tx.cuda(), g, dt)
     assert rel_err(out.float().cpu(), ref.float()) < 1e-3
+
+
+def test_scatter_epilogues_of_the_sequence_parallel_exchange():
+    """m4d_rmsnorm_scatter and m4d_attention_fwd_scatter (the fused Ulysses exchange) with LOCAL
+    destination buffers: bit-identical to the plain kernels followed by slicing."""
+    from more4d_b200 import ops
+    B, Ll, H, D, P = 2, 75, 4, 128, 2
+    C, gc = H * D, H * D // P
+    x = _rand((B, Ll, C), 41, 2.0).cuda()
+    w = (_rand((C,), 42, 0.1) + 1).cuda()
+    L = Ll * P
+    for r in range(P):                                    # this rank's tokens land at rows r*Ll..
+        dst = [torch.zeros(B, L, gc, device="cuda", dtype=BF16) for _ in range(P)]
+        ops.rmsnorm_scatter(x, w, dst, r * Ll, 1e-6)
+        ref = ops.rmsnorm_rope_(x.clone(), w, H, 1e-6)
+        for g in range(P):
+            assert torch.equal(dst[g][:, r * Ll:(r + 1) * Ll], ref[:, :, g * gc:(g + 1) * gc])
+            assert float(dst[g][:, :r * Ll].abs().sum()) == 0 and float(dst[g][:, (r + 1) * Ll:].abs().sum()) == 0
+    dst = [torch.zeros(B, L, gc, device="cuda", dtype=BF16) for _ in range(P)]
+    ops.rmsnorm_scatter(x, None, dst, 0, 1e-6)            # weight None: plain scatter copy
+    assert torch.equal(dst[1][:, :Ll], x[:, :, gc:])
+    # attention: 3 destinations of 100 rows cover Lq = 300 (ragged last tile), head columns 2..3 of 6
+    Bq, Lq, Lk, h, n_all = 2, 300, 333, 2, 6
+    q, k, v = _rand((Bq, Lq, h, D), 43).cuda(), _rand((Bq, Lk, h, D), 44).cuda(), _rand((Bq, Lk, h, D), 45).cuda()
+    kl = torch.tensor([333, 200], dtype=torch.int32, device="cuda")
+    ref = ops.attention(q, k, v, kl)
+    bufs = [torch.zeros(Bq, 100, n_all, D, device="cuda", dtype=BF16) for _ in range(3)]
+    ops.attention_scatter(q, k, v, [b_[:, :, 2:4] for b_ in bufs], kl)
+    for i, b_ in enumerate(bufs):
+        assert torch.equal(b_[:, :, 2:4], ref[:, i * 100:(i + 1) * 100])
+        assert float(b_[:, :, :2].abs().sum()) == 0 and float(b_[:, :, 4:].abs().sum()) == 0
