@@ -54,7 +54,14 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
 // bias (16-byte aligned vector loads), bf16 rounding (the reference's bf16 conv output), then
 // the residual add (ResidualBlock, vae:224) and its rounding.  `bias`, `res` point at the
 // chunk's first channel or are null.
-__device__ __forceinline__ void conv_chunk_values(const uint32_t* rr, const bf16* bias, const bf16* res,
+__device__ __forceinline__ void load_res_chunk(const bf16* res, uint4* r4) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r4[q] = reinterpret_cast<const uint4*>(res)[q];
+}
+
+// `res4`: the chunk's 32 residual values, already in registers (loaded one chunk ahead so their
+// latency overlaps the previous chunk / the wait for the accumulators), or null.
+__device__ __forceinline__ void conv_chunk_values(const uint32_t* rr, const bf16* bias, const uint4* res4,
                                                   float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
@@ -69,14 +76,11 @@ __device__ __forceinline__ void conv_chunk_values(const uint32_t* rr, const bf16
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-  if (res != nullptr) {
-    uint4 u4[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) u4[q] = reinterpret_cast<const uint4*>(res)[q];
+  if (res4 != nullptr) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float r8[8];
-      unpack8(u4[q], r8);
+      unpack8(res4[q], r8);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[q * 8 + e] = bf16_round(v[q * 8 + e] + r8[e]);
     }
@@ -140,7 +144,9 @@ __device__ __forceinline__ void conv_store_chunk(const ConvParams& p, const uint
     const int ch = n0 % p.n_split;
     const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
     float v[32];
-    conv_chunk_values(rr, p.bias ? p.bias + n0 : nullptr, p.residual ? p.residual + off : nullptr, v);
+    uint4 r4[4];
+    if (p.residual != nullptr) load_res_chunk(p.residual + off, r4);
+    conv_chunk_values(rr, p.bias ? p.bias + n0 : nullptr, p.residual ? r4 : nullptr, v);
     store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + off, v);
   } else {
     conv_store_chunk_slow(p, rr, t, h, w, n0);
