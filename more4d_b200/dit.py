@@ -68,6 +68,20 @@ def rope_params(max_seq_len: int, dim: int, theta: float = 10000.0) -> Tensor:
     return torch.polar(torch.ones_like(ang), ang)
 
 
+def rope_params_riflex(max_seq_len: int, dim: int, k: Optional[int] = None, L_test: Optional[int] = None,
+                       L_test_scale: Optional[float] = None, theta: float = 10000.0) -> Tensor:
+    """RIFLEx frame-axis table (t4d:264-320, `get_1d_rotary_pos_embed_riflex(..., use_real=False)`):
+    the k-th intrinsic frequency is lowered to 0.9 * 2 pi / L_test (/ L_test_scale) so that the
+    extrapolated clip stays inside one period.  Complex128 [max_seq_len, dim/2]."""
+    freqs = 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim))
+    if k is not None:
+        freqs[k - 1] = 0.9 * 2 * torch.pi / L_test
+    if L_test_scale is not None:
+        freqs[k - 1] = freqs[k - 1] / L_test_scale
+    ang = torch.outer(torch.arange(max_seq_len), freqs)
+    return torch.polar(torch.ones_like(ang), ang)
+
+
 def build_freqs(head_dim: int) -> Tensor:
     """The model's `freqs` buffer (t4d:928-935): frame | row | col tables along the pair axis."""
     d = head_dim
@@ -83,7 +97,8 @@ class _RopeCache:
         self.cos = self.sin = None
 
     def get(self, freqs: Tensor, device):
-        key = (freqs.data_ptr(), tuple(freqs.shape), str(device))
+        # the content tag guards against a re-allocated table (enable_riflex) landing on the same address
+        key = (freqs.data_ptr(), tuple(freqs.shape), str(device), float(freqs.real[-1].sum()))
         if key != self.key:
             f = freqs.to("cpu")
             self.cos = f.real.to(torch.float32).contiguous().to(device)
@@ -524,6 +539,18 @@ class WanTransformer4DModel(nn.Module):
         return self.patch_embedding.weight.dtype
 
     # cfg_skip bookkeeping of the reference (t4d:986-1008, cfg_optimization.py:5-39)
+    def enable_riflex(self, k=6, L_test=66, L_test_scale=4.886):
+        """t4d:1011-1025: swap the frame-axis RoPE table for its RIFLEx variant (length extrapolation).
+        The kernels read whatever table `self.freqs` holds."""
+        d = self.d
+        self.freqs = torch.cat([rope_params_riflex(1024, d - 4 * (d // 6), k=k, L_test=L_test,
+                                                   L_test_scale=L_test_scale),
+                                rope_params(1024, 2 * (d // 6)), rope_params(1024, 2 * (d // 6))], dim=1)
+
+    def disable_riflex(self):
+        """t4d:1027-1036."""
+        self.freqs = build_freqs(self.d)
+
     def enable_multi_gpus_inference(self, group=None):
         """t4d:1038-1044: shard ONE sample's sequence over the ranks of `group` (Ulysses).  Needs an
         initialised torch.distributed process group; num_heads must be a multiple of its size."""

@@ -180,3 +180,18 @@ def test_sequence_parallel_plan(rec):
     assert rec.calls["rmsnorm_rope_+rope"] == 2                                # ... RoPE after it (global positions)
     cross = [s for s in rec.attn_shapes if s[1][1] in (257, cfg.text_len)]
     assert all(s[0][1] == L // 2 for s in cross)                               # cross-attention stays token-local
+
+
+def test_riflex_changes_only_the_frame_axis_table():
+    cfg = WAN_TINY.with_(num_layers=1)
+    m = dit_mod.WanTransformer4DModel.from_config(cfg, device="meta")
+    base = m.freqs.clone()
+    m.enable_riflex(k=6, L_test=66, L_test_scale=4.886)
+    n_f = 128 // 2 - 2 * (128 // 6)                    # 22 frame-axis pairs, then 21 + 21
+    assert m.freqs.shape == base.shape and m.freqs.dtype == torch.complex128
+    diff = (m.freqs != base).any(dim=0)
+    assert diff[5] and int(diff.sum()) == 1 and 5 < n_f   # only intrinsic frequency k = 6 moved
+    import math
+    assert torch.allclose(m.freqs[1, 5].angle(), torch.tensor(0.9 * 2 * math.pi / 66 / 4.886, dtype=torch.float64))
+    m.disable_riflex()
+    assert torch.equal(m.freqs, base)

@@ -77,3 +77,23 @@ def test_install_3d_transformer_visim_backbone():
         with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
             ref(x=inp["x"], t=inp["t"], context=inp["context"], seq_len=inp["seq_len"],
                 clip_fea=inp["clip_fea"], y=inp["y"])
+
+
+def test_riflex_tables_match_reference():
+    """enable_riflex / disable_riflex (t4d:1011-1036): identical `freqs` tables to the reference's."""
+    from more4d_b200.config import WAN_TINY as cfg
+    from more4d_b200.dit import WanTransformer4DModel
+    t4d, _, _ = ref_import.load()
+    ref = t4d.WanTransformer4DModel(model_type="i2v", in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim,
+                                    num_heads=cfg.num_heads, num_layers=1, text_dim=cfg.text_dim,
+                                    text_len=cfg.text_len, add_ref_conv=True, use_dino_guidance=False,
+                                    use_omnimae_guidance=False)
+    ours = WanTransformer4DModel.from_config(cfg.with_(num_layers=1), device="meta")
+    assert torch.equal(ours.freqs, ref.freqs)
+    for kw in (dict(), dict(k=4, L_test=33, L_test_scale=2.0)):
+        ref.enable_riflex(**kw)
+        ours.enable_riflex(**kw)
+        assert ours.freqs.dtype == ref.freqs.dtype and torch.equal(ours.freqs, ref.freqs)
+    ref.disable_riflex()
+    ours.disable_riflex()
+    assert torch.equal(ours.freqs, ref.freqs)
