@@ -327,6 +327,19 @@ class AutoencoderKLWan(nn.Module):
         out = torch.stack([self._decode_one(u) for u in z])
         return DecoderOutput(out) if return_dict else (out,)
 
+    def _decode(self, zs: Tensor) -> DecoderOutput:
+        """vae:822-830 (already clamped to [-1, 1])."""
+        return self.decode(zs)
+
+    # The reference's "memory saver" entry points (vae:783-789,803-821,842-847 -> encode_full /
+    # decode_full, vae:549-676) run the same chunk loop under gradient checkpointing and are
+    # "functionally identical" forward (vae:551-552); here every path is the whole-sequence kernel
+    # formulation, which holds no per-chunk cache at all.
+    _encode_memory_saver = _encode
+    encode_memory_saver = encode
+    _decode_memory_saver = _decode
+    decode_memory_saver = decode
+
 
 class _Adaptor(nn.Module):
     kind = "encoder"
