@@ -85,6 +85,9 @@ def install_vae(ref):
     ref.decode = lambda z, return_dict=True: ours.decode(z, return_dict)
     ref._encode = ours._encode
     ref._decode = lambda zs: ours.decode(zs)
+    # the checkpointed "memory saver" twins (vae:783-821,842-847) are the same forward
+    ref.encode_memory_saver, ref.decode_memory_saver = ref.encode, ref.decode
+    ref._encode_memory_saver, ref._decode_memory_saver = ref._encode, ref._decode
     return ref
 
 
