@@ -534,6 +534,59 @@ class WanTransformer4DModel(nn.Module):
                    in_dim_ref_conv=cfg.in_dim_ref_conv,
                    use_spatial_guidance=cfg.use_spatial_guidance, device=device)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, transformer_additional_kwargs=None,
+                        low_cpu_mem_usage=False, torch_dtype=BF16, device=None):
+        """Checkpoint loading with the reference's rules (t4d:1393-1534; callers infer.py:537-565):
+        `config.json` supplies the constructor arguments (overridden / extended by
+        `transformer_additional_kwargs`, incl. its `dict_mapping` renames); weights come from
+        `diffusion_pytorch_model.bin|.safetensors` or every `*.safetensors` shard in the folder; a
+        `patch_embedding.weight` with fewer input channels than the model (the released 48-channel
+        Control checkpoint vs the 64-channel depth-conditioned model) is zero-padded; tensors whose
+        shape still differs are skipped; loading is non-strict.  `low_cpu_mem_usage` is accepted for
+        signature compatibility (parameters are created directly on `device`)."""
+        import glob
+        import inspect
+        import json
+        import os
+        if torch_dtype != BF16:
+            raise NotImplementedError("the B200 kernels run the reference's bf16 inference path only")
+        path = pretrained_model_path if subfolder is None else os.path.join(pretrained_model_path, subfolder)
+        cfg_file = os.path.join(path, "config.json")
+        if not os.path.isfile(cfg_file):
+            raise RuntimeError(f"{cfg_file} does not exist")
+        with open(cfg_file) as f:
+            config = json.load(f)
+        extra = dict(transformer_additional_kwargs or {})
+        for src, dst in extra.pop("dict_mapping", {}).items():
+            extra[dst] = config[src]
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self", "device"}
+        kwargs = {k: v for k, v in {**config, **extra}.items() if k in accepted}
+        model = cls(**kwargs, device=device)
+        files = [os.path.join(path, "diffusion_pytorch_model.bin"),
+                 os.path.join(path, "diffusion_pytorch_model.safetensors")]
+        if os.path.exists(files[0]):
+            state = torch.load(files[0], map_location="cpu")
+        else:
+            from safetensors.torch import load_file
+            shards = [files[1]] if os.path.exists(files[1]) else sorted(glob.glob(os.path.join(path, "*.safetensors")))
+            if not shards:
+                raise RuntimeError(f"no weights found under {path}")
+            state = {}
+            for shard in shards:
+                state.update(load_file(shard))
+        own = model.state_dict()
+        pe = state.get("patch_embedding.weight")
+        if pe is not None and pe.shape != own["patch_embedding.weight"].shape and \
+                pe.shape[1] < own["patch_embedding.weight"].shape[1] and pe.shape[0] == own["patch_embedding.weight"].shape[0]:
+            wide = torch.zeros(own["patch_embedding.weight"].shape, dtype=pe.dtype)
+            wide[:, :pe.shape[1]] = pe
+            state["patch_embedding.weight"] = wide
+        state = {k: v for k, v in state.items() if k in own and own[k].shape == v.shape}
+        missing, unexpected = model.load_state_dict(state, strict=False)
+        model.load_report = {"missing": list(missing), "unexpected": list(unexpected)}
+        return model
+
     @property
     def dtype(self):
         return self.patch_embedding.weight.dtype

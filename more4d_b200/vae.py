@@ -126,6 +126,22 @@ class AutoencoderKLWan(nn.Module):
         self._consts = None
         self.fuse_norms = True      # RMS_norm+SiLU in the producing conv's epilogue (96/192 channels)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, additional_kwargs=None, device=None):
+        """vae:849-871: a `.safetensors` / torch checkpoint of the inner model; keys get the `model.`
+        prefix; constructor arguments are filtered from `additional_kwargs`; non-strict load."""
+        import inspect
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self", "device", "cfg"}
+        model = cls(**{k: v for k, v in (additional_kwargs or {}).items() if k in accepted}, device=device)
+        if str(pretrained_model_path).endswith(".safetensors"):
+            from safetensors.torch import load_file
+            state = load_file(pretrained_model_path)
+        else:
+            state = torch.load(pretrained_model_path, map_location="cpu")
+        missing, unexpected = model.load_state_dict({"model." + k: v for k, v in state.items()}, strict=False)
+        model.load_report = {"missing": list(missing), "unexpected": list(unexpected)}
+        return model
+
     @property
     def dtype(self):
         return self.model.conv1.weight.dtype
