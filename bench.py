@@ -100,7 +100,14 @@ def cpu_reference_arm(args, cfg, L, grid, rank, repeats=1, skip=0):
     import torch
     from oracle import cpu_baseline
     rows = args.cpu_sample_rows
-    times, threads = cpu_baseline.time_block_sample(cfg, L, rows, grid, seed=0, repeats=max(1, repeats))
+    # all host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would
+    # otherwise time the reference arm on a single thread
+    try:
+        host_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_threads = os.cpu_count() or 1
+    times, threads = cpu_baseline.time_block_sample(cfg, L, rows, grid, seed=0, repeats=max(1, repeats),
+                                                    threads=host_threads)
     times = times[skip:] if len(times) > skip else times
     t_best = min(times)
     value = cpu_baseline.latent_steps_per_s(t_best, L, rows, cfg.num_layers)
