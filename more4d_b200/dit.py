@@ -182,7 +182,7 @@ class WanSelfAttention(nn.Module):
         (needs global token positions) and attention run; one all-to-all brings the output back."""
         B, n_loc, C = x.shape
         n, d = self.num_heads, self.head_dim
-        if sp.peer_memory and x.is_cuda:
+        if sp.peer_memory and x.device.type != "cpu":          # gloo / CPU tests take the collective form
             return self._attend_sp_peer(x, k_lens, grid_i32, cos, sin, sp)
         qkv = torch.empty(3, B, n_loc, C, device=x.device, dtype=BF16)
         for i, lin in enumerate((self.q, self.k, self.v)):

@@ -195,3 +195,64 @@ def test_riflex_changes_only_the_frame_axis_table():
     assert torch.allclose(m.freqs[1, 5].angle(), torch.tensor(0.9 * 2 * math.pi / 66 / 4.886, dtype=torch.float64))
     m.disable_riflex()
     assert torch.equal(m.freqs, base)
+
+
+class _FakePeerBuffers:
+    def __init__(self, B, L, C, P):
+        self.qkv = torch.empty(3, B, L, C // P, device="meta", dtype=BF16)
+        self.o = torch.empty(B, L // P, C, device="meta", dtype=BF16)
+        self.qkv_peers = [torch.empty(3, B, L, C // P, device="meta", dtype=BF16) for _ in range(P)]
+        self.o_peers = [torch.empty(B, L // P, C, device="meta", dtype=BF16) for _ in range(P)]
+        self.barriers = 0
+
+    def barrier(self):
+        self.barriers += 1
+
+
+def test_fused_peer_exchange_addressing(rec):
+    """The fused sequence-parallel exchange (dit._attend_sp_peer) on meta tensors: which kernel
+    writes which slice of which rank's buffer, for rank 1 of 2."""
+    cfg = WAN_TINY.with_(num_layers=1)
+    m = dit_mod.WanTransformer4DModel.from_config(cfg, device="meta")
+    attn = m.blocks[0].self_attn
+    B, n_loc, C, P, r = 2, 36, cfg.dim, 2, 1
+    H, d = cfg.num_heads, 128
+    h, gc, L = H // P, C // P, n_loc * P
+    pb = _FakePeerBuffers(B, L, C, P)
+
+    class SP:
+        world, rank, peer_memory = P, r, True
+
+        def peer_buffers(self, B_, L_, C_, device):
+            assert (B_, L_, C_) == (B, L, C)
+            return pb
+
+    v_outs, scat, att = [], [], []
+    orig_linear = rec.linear
+
+    def linear(x, weight, bias=None, epilogue=0, out=None, **kw):
+        if out is not None and out.shape == (n_loc, gc):
+            v_outs.append((tuple(weight.shape), out.storage_offset(), tuple(out.stride())))
+        return orig_linear(x, weight, bias, epilogue, out=out, **kw)
+
+    rec.linear = linear
+    rec.rmsnorm_scatter = lambda x, w, dst, row0, eps=1e-6: scat.append((tuple(x.shape), len(dst), tuple(dst[0].shape), row0))
+    rec.attention_scatter = lambda q, k, v, outs, k_lens=None: att.append(
+        (tuple(q.shape), tuple(k.shape), [(tuple(o.shape), tuple(o.stride()), o.storage_offset()) for o in outs]))
+    x = torch.empty(B, n_loc, C, device="meta", dtype=BF16)
+    cos = sin = torch.empty(1024, 64, device="meta")
+    out = attn.attend(x, torch.empty(B, device="meta", dtype=torch.int32),
+                      torch.empty(B, 3, device="meta", dtype=torch.int32), cos, sin, SP())
+    assert out is pb.o and pb.barriers == 2
+    # v: P destinations x B batches, each an [n_loc, C/P] GEMM into rows r*n_loc.. of slot 2
+    assert len(v_outs) == P * B
+    per_b = L * gc
+    want = sorted(2 * B * per_b + b * per_b + r * n_loc * gc for b in range(B))
+    assert sorted(o for _, o, _ in v_outs[:B]) == want and all(w == (gc, C) and s == (gc, 1) for w, _, s in v_outs)
+    # q, k: normalised locally, scattered by head group at row offset r*n_loc
+    assert scat == [((B, n_loc, C), P, (B, L, gc), r * n_loc)] * 2
+    # attention: all L queries of my h heads; chunk s goes to rank s at my head columns
+    (qs, ks, outs), = att
+    assert qs == (B, L, h, d) and ks == qs
+    assert outs == [((B, n_loc, h, d), (n_loc * C, C, d, 1), r * h * d)] * P
+    assert rec.calls["rmsnorm_rope_+rope"] == 2                      # RoPE after the exchange, on my heads
