@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  Nothing in ``more4d_b200/`` may import this package.
 Allowed importers: ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` — and there only as the checker / the CPU
-baseline, never as the thing shipped.
+baseline, never as the thing shipped.  (The development diagnostics under ``tools/`` use it the
+same way: as the checker of a probe, or as the CPU timing beside a GPU timing.)
 
 Contents
 --------
@@ -13,6 +14,9 @@ Contents
                 by the CPU tests (when the tree is present) to cross-check the restatement.
 ``dit_oracle``  torch-fp32 restatement of the Wan2.1-DiT forward (WanTransformer4DModel).
 ``vae_oracle``  torch-fp32 restatement of the causal Wan VAE + trajectory adaptors.
+``project_oracle``  numpy-float32 restatement of the z-buffer point projection
+                (``render_with_project``); reproduces the real function exactly on the goldens.
+``cpu_baseline``  bounded-sample timing of the DiT oracle for ``bench.py``.
 
 Parity pinning: the reference ships NO tests, golden vectors or fixtures,
 so parity is "unpinned by the reference's own tests".  The restatement is instead pinned
