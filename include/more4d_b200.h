@@ -49,8 +49,6 @@ int m4d_version(void);
 const char* m4d_error_string(int code);
 /* M4D_OK iff the current device is compute capability 10.x. */
 int m4d_device_check(void);
-/* Debug-only kernel variants (bit 0: swap V descriptor LBO/SBO, bit 1: swap P pack order). */
-void m4d_set_debug_flags(int flags);
 
 /* out[M,N] = epilogue(a[M,K] . w[N,K]^T + bias[N]) — tcgen05/TMEM GEMM, TMA-fed.
  * Replaces nn.Linear (cuBLAS) at wan_transformer4d.py:446-448,465 (self-attn q/k/v/o),
@@ -184,13 +182,6 @@ int m4d_conv3x3_rmsnorm_cl(const void* x, int T, int H, int W, int Cin, const vo
                            const void* bias, int kt, void* out, const void* residual,
                            const void* gamma, void* norm_out, int do_silu, void* stream);
 
-/* Direct conv for 3-channel planar inputs x bf16 [3, T, H, W] -> channels-last [T, H, W, Cout]:
- * Encoder3d.conv1 (wan_vae.py:289, kt = 3 causal) and the adaptors' conv_in
- * (trajectory_module.py:142, kt = 1); weights in the reference layout [Cout, 3, kt, 3, 3].
- * The input is read as x*in_scale + in_shift (`pseudo*2-1`, infer_vae.py:278). */
-int m4d_conv_in3(const void* x, const void* w, const void* bias, void* out, int T, int H, int W,
-                 int Cout, int kt, float in_scale, float in_shift, void* stream);
-
 /* RMS_norm over channels (* sqrt(C) * gamma) [+ SiLU] per pixel, in place allowed
  * (wan_vae.py:43-58 + nn.SiLU at :198-202). */
 int m4d_rmsnorm_silu_cl(const void* x, const void* gamma, void* out, long long pixels, int C,
@@ -225,6 +216,23 @@ int m4d_transpose_bf16(const void* in, void* out, int R, int C, long long ld_in,
 /* out bf16 = SiLU(x fp32), n % 4 == 0 — input of the Motion-Perception-Module projection
  * (wan_transformer4d.py:746-748,781). */
 int m4d_silu_bf16(const float* x, void* out, long long n, void* stream);
+
+/* ---- Motion-Perception-Module front end ---- */
+
+/* rows[(f*H+y)*W+x][tap*C + c] = act(in[f][y+dy-1][x+dx-1][c]) (zero outside), tap = dy*3+dx:
+ * the im2col operand that turns each Conv2d(768,768,3,padding=1) of `feature_adapter`
+ * (wan_transformer4d.py:888-892, applied at :1148 to the OmniMAE tokens viewed as [B,14,14,768])
+ * into one m4d_gemm_bf16 with the tap-major packed weight.  do_silu applies the nn.SiLU between
+ * the two convolutions on load (bf16 result, like the reference's bf16 activation).  C % 8 == 0. */
+int m4d_im2col3x3_cl(const void* in, void* rows, int F, int H, int W, int C, int do_silu, void* stream);
+
+/* F.interpolate(size=(H,W), mode='bilinear', align_corners=False) of in [B,h,w,C] channels-last
+ * (fp32 math, bf16 result) written to all T frames of out [B,T,H,W,C] — wan_transformer4d.py:
+ * 1149-1151 (`.unsqueeze(2).repeat(1,1,latent_T,1,1).flatten(2).transpose(1,2)` gives exactly
+ * this layout, [B, T*H*W, C]).  out_silu (or NULL) additionally receives bf16(SiLU(out)), the first
+ * op of every block's SpatialGuidanceModule.spatial_guide (:746-749); out may be NULL. */
+int m4d_bilinear_repeat_cl(const void* in, void* out, void* out_silu, int B, int h, int w, int C, int T,
+                           int H, int W, void* stream);
 
 /* ---- stage hand-off: point-cloud projection with a z-buffer ---- */
 

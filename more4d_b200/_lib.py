@@ -25,7 +25,6 @@ _SIGNATURES = {
     "m4d_version": (c_int, []),
     "m4d_error_string": (ctypes.c_char_p, [_I]),
     "m4d_device_check": (c_int, []),
-    "m4d_set_debug_flags": (None, [_I]),
     "m4d_gemm_bf16": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _P, _L, _P, _L, _I, _P]),
     "m4d_attention_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P,
                                   _F, _I, _P]),
@@ -46,7 +45,6 @@ _SIGNATURES = {
     "m4d_conv_cl": (c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P] + [_I] * 12 + [_P, _I, _I, _I, _I, _P,
                             _I, _I, _P, _P]),
     "m4d_conv3x3_rmsnorm_cl": (c_int, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
-    "m4d_conv_in3": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
     "m4d_rmsnorm_silu_cl": (c_int, [_P, _P, _P, _L, _I, _I, _P]),
     "m4d_upsample2x_cl": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "m4d_planar_to_cl": (c_int, [_P, _P, _L, _I, _I, _P, _P, _P]),
@@ -54,6 +52,8 @@ _SIGNATURES = {
     "m4d_groupnorm_swish_cl": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "m4d_softmax_rows": (c_int, [_P, _P, _I, _I, _L, _L, _F, _P]),
     "m4d_transpose_bf16": (c_int, [_P, _P, _I, _I, _L, _L, _P]),
+    "m4d_im2col3x3_cl": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "m4d_bilinear_repeat_cl": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "m4d_project_points_workspace": (c_longlong, [_L, _I, _I]),
     "m4d_project_points": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P]),
 }
@@ -81,11 +81,25 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        flags = os.environ.get("M4D_DEBUG_FLAGS")       # development only: kernel variant selection
-        if flags:
-            l.m4d_set_debug_flags(int(flags, 0))
         _lib = l
     return _lib
+
+
+def dev_set_flags(flags: int) -> None:
+    """Kernel-variant selection for A/B measurements.  Exists only in a development build
+    (`python more4d_b200/build.py --force -DM4D_DEV`); the product library exports no such symbol
+    and keeps no global mutable state."""
+    l = lib()
+    if not hasattr(l, "m4d_dev_set_flags"):
+        raise RuntimeError("this libmore4d_sm100.so is the product build: no development variants "
+                           "(rebuild with `python more4d_b200/build.py --force -DM4D_DEV`)")
+    l.m4d_dev_set_flags.restype = None
+    l.m4d_dev_set_flags.argtypes = [c_int]
+    l.m4d_dev_set_flags(int(flags))
+
+
+def is_dev_build() -> bool:
+    return hasattr(lib(), "m4d_dev_set_flags")
 
 
 def check(rc: int, what: str) -> None:

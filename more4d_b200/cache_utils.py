@@ -48,38 +48,59 @@ class TeaCache:
 
     @staticmethod
     def compute_rel_l1_distance(prev: torch.Tensor, cur: torch.Tensor) -> float:
-        return ((cur - prev).abs().mean() / prev.abs().mean()).cpu().item()
+        return _rel_l1(prev, cur)
 
     def reset(self):
-        self.cnt = 0
-        self.should_calc = True
-        self.accumulated_rel_l1_distance = 0
-        self.previous_modulated_input = None
-        self.previous_residual = None
-        self.previous_residual_cond = None
-        self.previous_residual_uncond = None
+        _reset(self)
 
     def decide(self, modulated_inp: torch.Tensor, cond_flag: bool) -> bool:
-        """The decision block of wan_transformer4d.py:1201-1220."""
-        if not cond_flag:
-            return self.should_calc
-        if self.cnt < self.num_skip_start_steps or self.previous_modulated_input is None:
-            should_calc = True        # (the reference would raise on a None previous input)
-            self.accumulated_rel_l1_distance = 0
-        else:
-            d = self.compute_rel_l1_distance(self.previous_modulated_input, modulated_inp)
-            self.accumulated_rel_l1_distance += self.rescale_func(d)
-            if self.accumulated_rel_l1_distance < self.rel_l1_thresh:
-                should_calc = False
-            else:
-                should_calc = True
-                self.accumulated_rel_l1_distance = 0
-        self.previous_modulated_input = modulated_inp
-        self.should_calc = should_calc
-        return should_calc
+        return teacache_decide(self, modulated_inp, cond_flag)
 
     def step_done(self, cond_flag: bool):
-        if cond_flag:
-            self.cnt += 1
-            if self.cnt == self.num_steps:
-                self.reset()
+        teacache_step_done(self, cond_flag)
+
+
+def _rel_l1(prev: torch.Tensor, cur: torch.Tensor) -> float:
+    return ((cur - prev).abs().mean() / prev.abs().mean()).cpu().item()
+
+
+def _reset(tc) -> None:
+    tc.cnt = 0
+    tc.should_calc = True
+    tc.accumulated_rel_l1_distance = 0
+    tc.previous_modulated_input = None
+    tc.previous_residual = None
+    tc.previous_residual_cond = None
+    tc.previous_residual_uncond = None
+
+
+def teacache_decide(tc, modulated_inp: torch.Tensor, cond_flag: bool) -> bool:
+    """The decision block of wan_transformer4d.py:1201-1220 as a free function over the FIELDS
+    of a TeaCache (`cnt`, `num_skip_start_steps`, `accumulated_rel_l1_distance`, `rescale_func`,
+    `rel_l1_thresh`, `previous_modulated_input`, `should_calc`): `tc` may be this module's class
+    or the reference's own MoRe4D/models/cache_utils.py:19-74 instance, which the pipeline /
+    infer.py create (`enable_teacache`, t4d:961-970) and `install()` hands over unchanged."""
+    if not cond_flag:
+        return tc.should_calc
+    if tc.cnt < tc.num_skip_start_steps or tc.previous_modulated_input is None:
+        should_calc = True            # (the reference would raise on a None previous input)
+        tc.accumulated_rel_l1_distance = 0
+    else:
+        d = _rel_l1(tc.previous_modulated_input, modulated_inp)
+        tc.accumulated_rel_l1_distance += tc.rescale_func(d)
+        if tc.accumulated_rel_l1_distance < tc.rel_l1_thresh:
+            should_calc = False
+        else:
+            should_calc = True
+            tc.accumulated_rel_l1_distance = 0
+    tc.previous_modulated_input = modulated_inp
+    tc.should_calc = should_calc
+    return should_calc
+
+
+def teacache_step_done(tc, cond_flag: bool) -> None:
+    """wan_transformer4d.py:1336-1339."""
+    if cond_flag:
+        tc.cnt += 1
+        if tc.cnt == tc.num_steps:
+            _reset(tc)

@@ -30,6 +30,7 @@ class DiTConfig:
     clip_dim: int = 1280
     clip_tokens: int = 257
     use_spatial_guidance: bool = False   # Motion-Perception-Module branch (t4d:739-783)
+    use_omnimae_guidance: bool = False   # + its front end: feature_adapter / resize / repeat (t4d:883-892,1127-1156)
     guidance_dim: int = 768
 
     @property

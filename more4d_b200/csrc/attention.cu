@@ -36,13 +36,14 @@ constexpr int A_TILE_BYTES = 128 * 128 * 2;   // 32 KB, stored as two [128 x 64]
 constexpr int A_HALF_BYTES = 128 * 64 * 2;    // 16 KB
 constexpr int A_THREADS = 384;
 constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024;
+#ifndef A_PIPE_D
+#define A_PIPE_D 3               // software-pipeline distance (pairs) between an EX2 and its consumers
+#endif
 
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
-constexpr int A_DEFAULT_VAR = 0;
-constexpr int A_DEFAULT_K64 = 0;              // 1: use the double-buffered 64-key-step kernel
-constexpr int A_DEFAULT_SPLIT = 0;            // 1: 16-softmax-warp kernel (two threads per row)
-constexpr int A_DEFAULT_PACE = 0;             // FFMA2 pacing distance in pairs (exp_pairs)
-constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe (measured: 0 is fastest)
+constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe
+constexpr int A_DEFAULT_MODE = 1;             // 1: sum-guarded speculative reference
+constexpr float A_SUM_GUARD = 65536.0f;       // MODE 1: a half tile whose row sum reaches 2^16 moves the reference
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
@@ -70,7 +71,8 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
 // 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split with a round-down
 // magic add, degree-3 minimax polynomial for 2^frac (rel. error ~1e-4, far below the bf16
 // rounding of P), exponent re-inserted with an integer add.  Offloads part of the softmax's
-// exponentials from the 16/clk/SM MUFU, which is otherwise co-critical with the tensor pipe.
+// exponentials from the 16/clk/SM MUFU, which is otherwise co-critical with the tensor pipe
+// (128 keys x 256 rows = 2048 MUFU clocks per step and SM sub-partition = the step's MMA time).
 __device__ __forceinline__ void ex2_emul2(float x0, float x1, float& r0, float& r1) {
   const float kMagic = 12582912.0f;              // 1.5 * 2^23
   x0 = fmaxf(x0, -126.0f);
@@ -91,42 +93,47 @@ __device__ __forceinline__ void ex2_emul2(float x0, float x1, float& r0, float& 
   r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-// c + 0 * dep: the value of c, but data-dependent on `dep` (ptxas cannot fold an IEEE 0 * x).
-__device__ __forceinline__ float pace_after(float dep, float c) {
-  float r;
-  asm("fma.rn.f32 %0, %1, 0f00000000, %2;" : "=f"(r) : "f"(dep), "f"(c));
-  return r;
+// p = 2^(s*c + neg_mc) for the logit pairs [Q0, Q0 + NQ) of a row (s = all 128 logits of the tile),
+// packed bf16x2 into pk[0 .. NQ); row-sum partials accumulate pairwise (FADD2) in pair order.
+// The consumers of pair q (FADD2 row sum, F2FP pack) are written A_PIPE_D pairs behind its two
+// EX2s: a warp issues in order, and consumers right behind their producers expose the MUFU
+// result latency on every pair (profiles/attn_r01c.md: 64 x [EX2, EX2, FADD2, F2FP] ran at ~20
+// instead of 16 clocks per pair).
+template <int PP, int Q0, int NQ>
+__device__ __forceinline__ void exp_pipe(const uint32_t* s, uint32_t* pk, float c, float neg_mc,
+                                         float& l0, float& l1) {
+  constexpr int D = A_PIPE_D;
+  float e0[NQ], e1[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ + D; ++i) {
+    if (i < NQ) {
+      const int q = Q0 + i;
+      float x0, x1;
+      fma2(x0, x1, __uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1]), c, c, neg_mc, neg_mc);
+      if ((q & 7) >= 8 - PP) {
+        ex2_emul2(x0, x1, e0[i], e1[i]);
+      } else {
+        e0[i] = fast_exp2(x0);
+        e1[i] = fast_exp2(x1);
+      }
+    }
+    if (i >= D) {
+      add2(l0, l1, e0[i - D], e1[i - D]);
+      pk[i - D] = pack_bf16(e0[i - D], e1[i - D]);
+    }
+  }
 }
 
-// p = 2^(s*c + neg_mc) for 64 logits -> 32 packed bf16x2 registers; PP of every 8 pairs use the
-// polynomial path.  Row-sum partials are accumulated pairwise (FADD2).
-//
-// Pacing: the MUFU issues one warp-wide EX2 per 8 clocks, so a row's 128 exponentials take
-// >= 1024 clocks and everything else (FFMA2 scale, FADD2 sum, bf16 pack) fits in the gaps — but
-// only if it is interleaved.  Left alone, ptxas hoists all independent FFMA2s to the front and
-// leaves a bare MUFU tail (profiles/attn_r01c: 64 x [EX2, EX2, FADD2, F2FP] = 1275 of the 1760
-// busy clocks per tile).  With PACE > 0 the scale operand of pair q is made data-dependent on
-// the EX2 result of pair q - PACE, which pins each FFMA2 into the gap after that EX2.
-template <int PP, int Q0, int Q1, int PACE>
-__device__ __forceinline__ void exp_pairs(const uint32_t* s, uint32_t* pk, float c, float neg_mc,
-                                          float& l0, float& l1) {
-  float hist[Q1 - Q0];
+// max over 32 logits (FMNMX3: two per instruction), keys >= valid excluded
+__device__ __forceinline__ float max32(const uint32_t* s, int valid, float m) {
+  float a = m, b = -INFINITY;
 #pragma unroll
-  for (int q = Q0; q < Q1; ++q) {
-    float x0, x1, p0, p1;
-    float cq = c;
-    if (PACE > 0 && q - Q0 >= PACE) cq = pace_after(hist[q - Q0 - PACE], c);
-    fma2(x0, x1, __uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1]), cq, cq, neg_mc, neg_mc);
-    if ((q & 7) >= 8 - PP) {
-      ex2_emul2(x0, x1, p0, p1);
-    } else {
-      p0 = fast_exp2(x0);
-      p1 = fast_exp2(x1);
-    }
-    hist[q - Q0] = p1;
-    add2(l0, l1, p0, p1);
-    pk[q] = pack_bf16(p0, p1);
+  for (int i = 0; i < 32; i += 4) {
+    a = max3(a, i < valid ? __uint_as_float(s[i]) : -INFINITY, i + 1 < valid ? __uint_as_float(s[i + 1]) : -INFINITY);
+    b = max3(b, i + 2 < valid ? __uint_as_float(s[i + 2]) : -INFINITY,
+             i + 3 < valid ? __uint_as_float(s[i + 3]) : -INFINITY);
   }
+  return fmaxf(a, b);
 }
 
 struct AttnParams {
@@ -136,7 +143,6 @@ struct AttnParams {
   const int* k_lens;                      // [B] or null
   float scale_log2;                       // softmax_scale * log2(e)
   int accumulate;                         // out = bf16(out + bf16(o))  (summed cross-attention)
-  int flags;                              // debug variants, see m4d_set_debug_flags
   // scatter epilogue (sequence-parallel exchange fused into the attention epilogue): query row l
   // is stored to out_scatter[l / scatter_rows] at row l % scatter_rows — the destinations are
   // the ranks' receive buffers (peer memory), one launch serves all of them
@@ -144,13 +150,13 @@ struct AttnParams {
   int scatter_rows;                       // 0 = plain output
 };
 
-// VAR = 0: P is handed to the tensor pipe in two 64-key halves; VAR = 1: in four 32-key
-// quarters (finer PV / exp overlap, more barrier traffic).  Measured variants that did NOT
-// help on the B200 and were removed again: one mbarrier arrival per warp instead of per thread
-// (-4 %), loading the second half of S while max-reducing the first (-1 %), polynomial exp2 on
-// the FMA pipe for 12-50 % of the logits (PP > 0: -4 .. -11 %, the softmax is latency-, not
-// MUFU-bound), and the double-buffered 64-key-step kernel below (-25 %).
-template <int PP, int VAR, int PACE>
+// PP: pairs of every 8 whose exponential runs on the FMA pipe (ex2_emul2); MODE 0: exact row max
+// before the exponentials, MODE 1: sum-guarded speculative reference (see the softmax section).  P is handed to the tensor pipe in two 64-key halves.
+// Measured variants that did NOT help on the B200 and were removed again (round 1,
+// profiles/attn_variant_sweep_r01.log): one mbarrier arrival per warp instead of per thread
+// (-4 %), P in 1 or 4 slices, 64-key steps with a double-buffered S (-25 %: N=64 QK MMAs are
+// shared-memory bound), two threads per row (16 softmax warps share the MUFU: -9 %).
+template <int PP, int MODE>
 __global__ void __launch_bounds__(A_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -167,7 +173,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* v_full = k_empty + A_KS;    // A_VS
   uint64_t* v_empty = v_full + A_VS;    // A_VS
   uint64_t* s_full = v_empty + A_VS;    // 2
-  uint64_t* p_ready = s_full + 2;       // 2 tiles x up to 4 key-slices: [t * 4 + slice]
+  uint64_t* p_ready = s_full + 2;       // per tile t: [4t + 0/1] P halves ready, [4t + 2] PV of the first half done
   uint64_t* o_final = p_ready + 8;      // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
@@ -200,7 +206,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      for (int i = 0; i < 4; ++i) mbar_init(&p_ready[4 * t + i], 128);
+      for (int i = 0; i < 4; ++i) mbar_init(&p_ready[4 * t + i], i == 2 ? 1 : 128);   // [2]: pv_half, by commit
       mbar_init(&o_final[t], 1);
     }
     fence_mbar_init();
@@ -260,7 +266,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       };
       // O_t += P_t[:, slice] V[slice, :] — P arrives in NS key-slices so the first PV MMAs
       // overlap the exponentials of the later slices
-      constexpr int NS = (VAR == 1) ? 4 : (VAR == 2 ? 1 : 2);
+      constexpr int NS = 2;
       auto issue_pv_tile = [&](int t, int sv, int j, bool leader) {   // whole warp
         const uint32_t b_lo = v_lo + sv * (A_TILE_BYTES >> 4);
 #pragma unroll
@@ -274,6 +280,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               umma_ts(tO0 + t * 128, tS0 + t * 128 + kk * 8, dp(b_lo + kk * (2048 >> 4), HI), idesc_pv,
                       !(j == 0 && kk == 0));
             }
+            // MODE 1: a softmax warp whose SECOND P half needs a new reference must rescale O
+            // after these MMAs and before the next ones (rare; nobody waits otherwise)
+            if (MODE == 1 && sl == 0) umma_commit(&p_ready[4 * t + 2]);
           }
           __syncwarp();
         }
@@ -324,6 +333,27 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
+    // Per 128-key step and query tile the chain  S ready -> P ready -> PV -> QK(next) -> S ready
+    // bounds the step (TMEM is full, so S(j+1) cannot be produced while P(j) is live); the
+    // softmax part of it is kept as short as the MUFU allows.
+    //
+    // MODE 1 — sum-guarded speculative reference.  Softmax is invariant to the reference r in
+    // p = 2^(s*c - r) as long as nothing over- or underflows, so the row max need not be known:
+    // the exponentials of tile j start against the reference left by the earlier tiles the moment
+    // the first 32 logits arrive from TMEM (no max pass: 64 FMNMX3 and ~235 clocks per tile less),
+    // and the row sum they produce anyway is the guard: a half tile whose sum stays below 2^16
+    // (no inf / NaN either) proves every p < 2^16 and is handed to the tensor pipe as it is.
+    // Otherwise (always at j = 0, rarely later) the rows concerned take the exact path: reload
+    // S — still intact in TMEM —, reduce the true max, move the reference, rescale O / l, redo the
+    // half.  For the SECOND half the first one is already with the tensor pipe at the old
+    // reference: the warp waits for those MMAs (`pv_half`, committed by the MMA warp on every step
+    // and waited on only here) before it rescales O.  The reference never exceeds the running row
+    // max, so nothing underflows that the textbook form would keep.
+    // MODE 0 — exact: max pass over the tile first, lazy rescale (threshold 2^8), then the
+    // exponentials; kept as the baseline of the measurement.
+    // In both modes a row's result depends on its own logits only (per-row decisions, fixed
+    // MUFU / polynomial assignment per key column, fixed summation order): any query chunking —
+    // the sequence-parallel launches — is bit-identical.
     reg_inc<208>();
     const int t = warp >> 2;                       // query tile
     const int quad = warp & 3;
@@ -332,110 +362,193 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tS = tmem_base + lane_base + t * 128;
     const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
     const float c = p.scale_log2;
-    float m_used = -INFINITY;
+    uint32_t pr0;      // opaque to the compiler, otherwise it re-derives the address late (and the arrive with it)
+    asm volatile("mov.u32 %0, %1;" : "=r"(pr0) : "r"(smem_u32(&p_ready[4 * t + 0])));
+    float m_used = -INFINITY;                      // reference, in logit units (r = m_used * c)
     float l_sum = 0.f;
+
+    // O *= f, by 32-column chunks (rare path)
+    auto rescale_o = [&](float f) {
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(tO + cc * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+        tmem_st32(tO + cc * 32, o);
+      }
+      tmem_st_wait();
+    };
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       uint32_t s[128];
-      tmem_ld32(tS + 0, s + 0);
-      tmem_ld32(tS + 32, s + 32);
-      tmem_ld32(tS + 64, s + 64);
-      tmem_ld32(tS + 96, s + 96);
-      tmem_ld_wait();
-      reg_fence32(s + 0);
-      reg_fence32(s + 32);
-
+      uint32_t ph[32];
       const int valid = kv_len - j * A_BKV;        // keys of this tile that exist
-      if (valid < 64) {
+      float l0 = 0.f, l1 = 0.f;
+      if (MODE == 1) {
+        // ---- first half, speculative
+        tmem_ld32(tS + 0, s + 0);
+        tmem_ld_wait();                            // chunk 0 has landed
+        tmem_ld32(tS + 32, s + 32);                // in flight while chunk 0 is processed
+        tmem_ld32(tS + 64, s + 64);
+        tmem_ld32(tS + 96, s + 96);
+        reg_fence32(s + 0);
+        if (valid < 32) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= valid) s[i] = 0xFF800000u;      // -inf
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+          for (int i = 0; i < 32; ++i)
+            if (i >= valid) s[i] = 0xFF800000u;    // -inf
+        }
+        float neg_mc = -m_used * c;
+        exp_pipe<PP, 0, 16>(s, ph, c, neg_mc, l0, l1);
+        tmem_ld_wait();
+        reg_fence32(s + 32);
+        reg_fence32(s + 64);
+        reg_fence32(s + 96);
+        if (valid < A_BKV) {
 #pragma unroll
-      for (int i = 4; i < 60; i += 8) {        // FMNMX3: two logits per instruction
-        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-      }
-      mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
-      mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
-      reg_fence32(s + 64);
-      reg_fence32(s + 96);
-      if (valid < A_BKV) {
-#pragma unroll
-        for (int i = 64; i < 128; ++i)
-          if (i >= valid) s[i] = 0xFF800000u;
-      }
-#pragma unroll
-      for (int i = 64; i < 128; i += 8) {
-        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const float m_new = fmaxf(m_used, mx);
-        const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, grow)) {
-          // only rows that crossed the threshold THEMSELVES move their reference max: a row's
-          // result then depends on its own logits alone, not on which 31 rows share its warp,
-          // so chunking the queries differently (sequence-parallel launches) is bit-identical
-          const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;
-          if (grow) m_used = m_new;
-          l_sum *= f;
+          for (int i = 32; i < 128; ++i)
+            if (i >= valid) s[i] = 0xFF800000u;
+        }
+        exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
+        if (__any_sync(0xffffffffu, !(l0 + l1 < A_SUM_GUARD))) {
+          // exact path for the whole tile: S is intact (nothing of this tile has been stored);
+          // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled
+          const bool mine = !(l0 + l1 < A_SUM_GUARD);
+          float mxr = -INFINITY;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
             uint32_t o[32];
-            tmem_ld32(tO + cc * 32, o);
+            tmem_ld32(tS + cc * 32, o);
             tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(tO + cc * 32, o);
+            mxr = max32(o, valid - cc * 32, mxr);
           }
-          tmem_st_wait();
-        }
-      }
-      const float neg_mc = -m_used * c;
-      float l0 = 0.f, l1 = 0.f;
-      if (VAR == 1) {
+          float f = 1.0f;
+          if (mine) {
+            const float m_new = fmaxf(m_used, mxr);
+            f = (j == 0) ? 0.f : fast_exp2((m_used - m_new) * c);
+            m_used = m_new;
+            l_sum *= f;
+          }
+          if (j > 0) rescale_o(f);                 // warp-collective tcgen05 ops: every lane takes part
+          neg_mc = -m_used * c;
+          tmem_ld32(tS + 0, s + 0);
+          tmem_ld32(tS + 32, s + 32);
+          tmem_ld_wait();
+          reg_fence32(s + 0);
+          reg_fence32(s + 32);
+          if (valid < 64) {
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          uint32_t pq[16];
-          exp_pairs<PP, 0, 16, PACE>(s + sl * 32, pq, c, neg_mc, l0, l1);
-          tmem_st16(tS + sl * 16, pq);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&p_ready[4 * t + sl]);
+            for (int i = 0; i < 64; ++i)
+              if (i >= valid) s[i] = 0xFF800000u;
+          }
+          l0 = 0.f;
+          l1 = 0.f;
+          exp_pipe<PP, 0, 32>(s, ph, c, neg_mc, l0, l1);
         }
-      } else if (VAR == 2) {
-        uint32_t pa[32], pb[32];
-        exp_pairs<PP, 0, 32, PACE>(s, pa, c, neg_mc, l0, l1);
-        tmem_st32(tS, pa);
-        exp_pairs<PP, 0, 32, PACE>(s + 64, pb, c, neg_mc, l0, l1);
-        tmem_st32(tS + 32, pb);
+        tmem_st32(tS, ph);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[4 * t]);
-      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pr0) : "memory");
+        // ---- second half
+        float h0 = 0.f, h1 = 0.f;
+        exp_pipe<PP, 32, 32>(s, ph, c, neg_mc, h0, h1);
+        if (__any_sync(0xffffffffu, !(h0 + h1 < A_SUM_GUARD))) {
+          // the first half is with the tensor pipe at the old reference: wait for its MMAs,
+          // then move the reference (true max of the second half), rescale O / l, redo the half
+          const bool mine = !(h0 + h1 < A_SUM_GUARD);
+          mbar_wait(&p_ready[4 * t + 2], j & 1);
+          tc_fence_after();
+          float mxr = -INFINITY;
+#pragma unroll 1
+          for (int cc = 2; cc < 4; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tS + cc * 32, o);
+            tmem_ld_wait();
+            mxr = max32(o, valid - cc * 32, mxr);
+          }
+          float f = 1.0f;
+          if (mine) {
+            const float m_new = fmaxf(m_used, mxr);
+            f = fast_exp2((m_used - m_new) * c);
+            m_used = m_new;
+            l_sum *= f;
+            l0 *= f;
+            l1 *= f;
+          }
+          rescale_o(f);
+          neg_mc = -m_used * c;
+          tmem_ld32(tS + 64, s + 64);
+          tmem_ld32(tS + 96, s + 96);
+          tmem_ld_wait();
+          reg_fence32(s + 64);
+          reg_fence32(s + 96);
+          if (valid < A_BKV) {
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          uint32_t ph[32];
-          exp_pairs<PP, 0, 32, PACE>(s + sl * 64, ph, c, neg_mc, l0, l1);
-          tmem_st32(tS + sl * 32, ph);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&p_ready[4 * t + sl]);
+            for (int i = 64; i < 128; ++i)
+              if (i >= valid) s[i] = 0xFF800000u;
+          }
+          h0 = 0.f;
+          h1 = 0.f;
+          exp_pipe<PP, 32, 32>(s, ph, c, neg_mc, h0, h1);
         }
+        tmem_st32(tS + 32, ph);
+        tmem_st_wait();
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+8];" ::"r"(pr0) : "memory");
+        l_sum += (l0 + l1) + (h0 + h1);
+      } else {
+        // ---- MODE 0: exact max first
+        tmem_ld32(tS + 0, s + 0);
+        tmem_ld32(tS + 32, s + 32);
+        tmem_ld32(tS + 64, s + 64);
+        tmem_ld32(tS + 96, s + 96);
+        tmem_ld_wait();
+        reg_fence32(s + 0);
+        reg_fence32(s + 32);
+        reg_fence32(s + 64);
+        reg_fence32(s + 96);
+        if (valid < A_BKV) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) s[i] = 0xFF800000u;
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+          mx[0] = max3(mx[0], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+          mx[1] = max3(mx[1], __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          mx[2] = max3(mx[2], __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+          mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+        }
+        const float mxr = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (j == 0) {
+          m_used = mxr;
+        } else {
+          const float m_new = fmaxf(m_used, mxr);
+          const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;
+            if (grow) m_used = m_new;
+            l_sum *= f;
+            rescale_o(f);
+          }
+        }
+        const float neg_mc = -m_used * c;
+        exp_pipe<PP, 0, 32>(s, ph, c, neg_mc, l0, l1);
+        tmem_st32(tS, ph);
+        tmem_st_wait();
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pr0) : "memory");
+        exp_pipe<PP, 32, 32>(s, ph, c, neg_mc, l0, l1);
+        tmem_st32(tS + 32, ph);
+        tmem_st_wait();
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+8];" ::"r"(pr0) : "memory");
+        l_sum += l0 + l1;
       }
-      l_sum += l0 + l1;
     }
 
     // ---- epilogue: O / l -> bf16 -> global
@@ -489,617 +602,6 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 10) tmem_dealloc<512>(tmem_base);
 }
 
-
-// =======================================================================================
-// Variant "k64": 64-key steps with DOUBLE-BUFFERED S per query tile.
-//
-// In the kernel above S_t(j+1) cannot be produced before P_t(j) has been consumed (P aliases S
-// and TMEM is full: S0|S1|O0|O1), so each query tile runs the serial chain
-// softmax -> PV -> QK -> softmax and the tensor pipe idles while a tile is in its softmax.
-// Here a step covers 64 keys, so S_t fits twice in the same 128 columns (S[t][0] | S[t][1]):
-// QK_t(j+1) is issued BEFORE PV_t(j) and lands in the other buffer while softmax_t(j) is still
-// running — the softmax warpgroups never wait for the tensor pipe and vice versa.  Costs: the
-// N=64 QK MMAs re-read the 4 KB Q slice per 64 keys (shared-memory bound, ~1.5x their ideal
-// time) and barrier traffic doubles.  O-rescale needs PV_t(j-1) to have finished, which is no
-// longer implied by "S_t(j) ready": a pv_done barrier is waited on only when a rescale happens.
-// TMEM columns: S[t][u] at (2t+u)*64, P[t][u] aliases its first 32 columns, O_t at 256 + 128 t.
-// =======================================================================================
-constexpr int B_BKV = 64;
-constexpr int B_KS = 4, B_VS = 4;
-constexpr int B_KV_TILE = B_BKV * 128 * 2;     // 16 KB = two [64 x 64] SW128 halves of 8 KB
-constexpr int B_KV_HALF = B_BKV * 64 * 2;
-constexpr int B_SMEM_BYTES = A_NQ * A_TILE_BYTES + (B_KS + B_VS) * B_KV_TILE + 256 + 1024;
-
-__global__ void __launch_bounds__(A_THREADS, 1)
-attn_fwd_d128_k64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                         const __grid_constant__ CUtensorMap tmV, AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + A_NQ * A_TILE_BYTES;
-  uint8_t* sV = sK + B_KS * B_KV_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + B_VS * B_KV_TILE);
-  uint64_t* q_full = bars;               // 1
-  uint64_t* k_full = q_full + 1;         // B_KS
-  uint64_t* k_empty = k_full + B_KS;     // B_KS
-  uint64_t* v_full = k_empty + B_KS;     // B_VS
-  uint64_t* v_empty = v_full + B_VS;     // B_VS
-  uint64_t* s_full = v_empty + B_VS;     // [t*2 + u]
-  uint64_t* p_ready = s_full + 4;        // [t*2 + u]
-  uint64_t* pv_done = p_ready + 4;       // [t]
-  uint64_t* o_final = pv_done + 2;       // [t]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-
-  int kv_len = p.Lk;
-  if (p.k_lens != nullptr) {
-    int kl = p.k_lens[b];
-    kv_len = kl < kv_len ? kl : kv_len;
-  }
-  if (kv_len < 1) kv_len = 1;
-  const int n_kv = (kv_len + B_BKV - 1) / B_BKV;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 9 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < B_KS; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-    }
-    for (int s = 0; s < B_VS; ++s) {
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&pv_done[t], 1);
-      mbar_init(&o_final[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 10) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 8) {
-    reg_dec<80>();
-    if (warp == 8 && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
-      for (int t = 0; t < A_NQ; ++t)
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sQ + t * A_TILE_BYTES + h * A_HALF_BYTES, &tmQ, q_full, h * 64, head,
-                      q_blk * (A_NQ * A_BQ) + t * A_BQ, b);
-      auto load_k = [&](int j) {
-        const int sk = j % B_KS;
-        mbar_wait(&k_empty[sk], ((j / B_KS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[sk], B_KV_TILE);
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sK + sk * B_KV_TILE + h * B_KV_HALF, &tmK, &k_full[sk], h * 64, head, j * B_BKV, b);
-      };
-      auto load_v = [&](int j) {
-        const int sv = j % B_VS;
-        mbar_wait(&v_empty[sv], ((j / B_VS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[sv], B_KV_TILE);
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sV + sv * B_KV_TILE + h * B_KV_HALF, &tmV, &v_full[sv], h * 64, head, j * B_BKV, b);
-      };
-      load_k(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) load_k(j + 1);
-        load_v(j);
-      }
-    } else if (warp == 9 && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      auto issue_qk = [&](int t, int sk, int u) {
-        const uint32_t d = tmem_base + (t * 2 + u) * 64;
-#pragma unroll
-        for (int kk = 0; kk < A_D / 16; ++kk) {
-          const uint64_t ad = umma_smem_desc(
-              q_addr + t * A_TILE_BYTES + (kk >> 2) * A_HALF_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_smem_desc(
-              k_addr + sk * B_KV_TILE + (kk >> 2) * B_KV_HALF + (kk & 3) * 32, 16, 1024);
-          umma_ss(d, ad, bd, idesc_qk, kk != 0);
-        }
-      };
-      auto issue_pv = [&](int t, int sv, int u, bool first) {
-        const uint32_t a = tmem_base + (t * 2 + u) * 64;
-        const uint32_t d = tmem_base + 256 + t * 128;
-#pragma unroll
-        for (int kk = 0; kk < B_BKV / 16; ++kk) {
-          const uint64_t bd = umma_smem_desc(v_addr + sv * B_KV_TILE + kk * 2048, B_KV_HALF, 1024);
-          umma_ts(d, a + kk * 8, bd, idesc_pv, !(first && kk == 0));
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0, 0);
-      umma_commit(&s_full[0]);
-      issue_qk(1, 0, 0);
-      umma_commit(&s_full[2]);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int u = j & 1;
-        const bool last = (j + 1 == n_kv);
-        if (!last) {
-          const int sk = (j + 1) % B_KS;
-          mbar_wait(&k_full[sk], ((j + 1) / B_KS) & 1);
-          tc_fence_after();
-          issue_qk(0, sk, u ^ 1);
-          umma_commit(&s_full[0 + (u ^ 1)]);
-          issue_qk(1, sk, u ^ 1);
-          umma_commit(&s_full[2 + (u ^ 1)]);
-          umma_commit(&k_empty[sk]);
-        }
-        const int sv = j % B_VS;
-        mbar_wait(&v_full[sv], (j / B_VS) & 1);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_ready[t * 2 + u], (j >> 1) & 1);
-          tc_fence_after();
-          issue_pv(t, sv, u, j == 0);
-          umma_commit(&pv_done[t]);
-          if (last) umma_commit(&o_final[t]);
-        }
-        umma_commit(&v_empty[sv]);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    reg_inc<208>();
-    const int t = warp >> 2;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
-    const float c = p.scale_log2;
-    float m_used = -INFINITY;
-    float l_sum = 0.f;
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int u = j & 1;
-      const uint32_t tS = tmem_base + lane_base + (t * 2 + u) * 64;
-      mbar_wait(&s_full[t * 2 + u], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t s[64];
-      tmem_ld32(tS + 0, s + 0);
-      tmem_ld32(tS + 32, s + 32);
-      tmem_ld_wait();
-      reg_fence32(s + 0);
-      reg_fence32(s + 32);
-      const int valid = kv_len - j * B_BKV;
-      if (valid < B_BKV) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= valid) s[i] = 0xFF800000u;
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int i = 4; i < 60; i += 8) {
-        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-      }
-      mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
-      mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const float m_new = fmaxf(m_used, mx);
-        const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&pv_done[t], (j - 1) & 1);       // PV_t(j-1) must have landed in O_t
-          tc_fence_after();
-          const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;   // per-row, see the main kernel
-          if (grow) m_used = m_new;
-          l_sum *= f;
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t o[32];
-            tmem_ld32(tO + cc * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(tO + cc * 32, o);
-          }
-          tmem_st_wait();
-        }
-      }
-      const float neg_mc = -m_used * c;
-      float l0 = 0.f, l1 = 0.f;
-      uint32_t pk[32];
-      exp_pairs<0, 0, 32, 0>(s, pk, c, neg_mc, l0, l1);
-      tmem_st32(tS, pk);
-      l_sum += l0 + l1;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[t * 2 + u]);
-    }
-
-    mbar_wait(&o_final[t], 0);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
-    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
-    const bool row_ok = q_row < p.Lq;
-    bf16* orow = p.out + static_cast<long long>(b) * p.out_stride_b +
-                 static_cast<long long>(q_row) * p.out_stride_l + head * A_D;
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t o[32];
-      tmem_ld32(tO + cc * 32, o);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
-          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
-          if (p.accumulate) {
-            const uint4 prev = *dst;
-            const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
-              v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
-            }
-          }
-          uint4 ov;
-          ov.x = pack_bf16(v[0], v[1]);
-          ov.y = pack_bf16(v[2], v[3]);
-          ov.z = pack_bf16(v[4], v[5]);
-          ov.w = pack_bf16(v[6], v[7]);
-          *dst = ov;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 10) tmem_dealloc<512>(tmem_base);
-}
-
-
-// =======================================================================================
-// Variant "split": SIXTEEN softmax warps — two threads per query row, 64 keys each.
-//
-// In the kernel at the top one thread owns a whole 128-key row, and the per-tile chain
-// S ready -> [tcgen05.ld, max pass, scale, 128 EX2] -> P ready -> PV -> QK -> S ready is what
-// bounds the period: sampling (profiles/attn_r01c.md) shows 1760 busy clocks per tile-step in
-// the softmax warps, of which only 1024 are MUFU-bound; the rest is the serial in-order
-// instruction stream of ONE warp per scheduler (max pass 235, FFMA2 block 235, loads / stores /
-// barriers).  Here the two warpgroups of a tile split the columns: the MUFU work per tile is
-// unchanged (the two warps of a scheduler share the pipe) but every other part of the chain is
-// done by twice as many threads, with the same total instruction count — the kernel is
-// power-capped, so trading energy for cycles (polynomial exp2, pacing) does not pay, shortening
-// the chain at equal work should.  MEASURED: it does not (profiles/attn_split_r01.md: 7.22 M vs
-// 6.63 M cycles, tensor pipe 65 % vs 71 %, 1170 vs 1260-1290 TF/s): the partner warps w and
-// w + 4 sit on the SAME scheduler, whose issue slot and MUFU were the busy resources, so the
-// per-tile softmax takes as long as before plus the exchange.  Kept as a debug variant
-// (flags 0x6000000), default off.  Costs: one 64-thread named barrier + a 2-float exchange per
-// row and step for the row max, and 104 instead of 208 registers per softmax thread.
-// Warps: 0-7 tile 0 (0-3 keys 0-63, 4-7 keys 64-127), 8-15 tile 1, 16 TMA, 17 MMA, 18 TMEM.
-// =======================================================================================
-constexpr int C_THREADS = 640;
-constexpr int C_XCH_FLOATS = 2 * 2 * 2 * 128 + 2 * 2 * 128;      // max exchange (double-buffered) + l exchange
-constexpr int C_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + C_XCH_FLOATS * 4 + 256 + 1024;
-
-__global__ void __launch_bounds__(C_THREADS, 1)
-attn_fwd_d128_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                           const __grid_constant__ CUtensorMap tmV, AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + A_NQ * A_TILE_BYTES;
-  uint8_t* sV = sK + A_KS * A_TILE_BYTES;
-  float* xch = reinterpret_cast<float*>(sV + A_VS * A_TILE_BYTES);      // [parity][tile][half][row]
-  float* lxch = xch + 2 * 2 * 2 * 128;                                 // [tile][half][row]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + C_XCH_FLOATS);
-  uint64_t* q_full = bars;              // 1
-  uint64_t* k_full = q_full + 1;        // A_KS
-  uint64_t* k_empty = k_full + A_KS;    // A_KS
-  uint64_t* v_full = k_empty + A_KS;    // A_VS
-  uint64_t* v_empty = v_full + A_VS;    // A_VS
-  uint64_t* s_full = v_empty + A_VS;    // 2
-  uint64_t* p_ready = s_full + 2;       // [t * 2 + half]
-  uint64_t* o_final = p_ready + 4;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-
-  int kv_len = p.Lk;
-  if (p.k_lens != nullptr) {
-    int kl = p.k_lens[b];
-    kv_len = kl < kv_len ? kl : kv_len;
-  }
-  if (kv_len < 1) kv_len = 1;
-  const int n_kv = (kv_len + A_BKV - 1) / A_BKV;
-
-  if (warp == 16 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 17 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < A_KS; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-    }
-    for (int s = 0; s < A_VS; ++s) {
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_ready[2 * t], 128);
-      mbar_init(&p_ready[2 * t + 1], 128);
-      mbar_init(&o_final[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 18) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 16) {
-    // ------------------------------------------------------------------ data movement + MMA
-    // setmaxnreg.inc only draws on registers released by setmaxnreg.dec in the same CTA: the
-    // 4 x 128 x (104 - 96) = 4096 the softmax warpgroups ask for must be covered by this
-    // warpgroup's 128 x (96 - 56) = 5120 (with dec<80> the last inc blocks forever)
-    reg_dec<56>();
-    if (warp == 16 && lane == 0) {
-      mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
-      for (int t = 0; t < A_NQ; ++t)
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sQ + t * A_TILE_BYTES + h * A_HALF_BYTES, &tmQ, q_full, h * 64, head,
-                      q_blk * (A_NQ * A_BQ) + t * A_BQ, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int sk = j % A_KS, sv = j % A_VS;
-        mbar_wait(&k_empty[sk], ((j / A_KS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[sk], A_TILE_BYTES);
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sK + sk * A_TILE_BYTES + h * A_HALF_BYTES, &tmK, &k_full[sk], h * 64, head,
-                      j * A_BKV, b);
-        mbar_wait(&v_empty[sv], ((j / A_VS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[sv], A_TILE_BYTES);
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sV + sv * A_TILE_BYTES + h * A_HALF_BYTES, &tmV, &v_full[sv], h * 64, head,
-                      j * A_BKV, b);
-      }
-    } else if (warp == 17) {
-      // same issue scheme as attn_fwd_d128_kernel: converged warp, one elected lane
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
-      constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFF) | (1u << 16);
-      const uint32_t k_lo = ((smem_u32(sK) >> 4) & 0x3FFF) | (1u << 16);
-      const uint32_t v_lo = ((smem_u32(sV) >> 4) & 0x3FFF) | ((A_HALF_BYTES >> 4) << 16);
-      const uint32_t tS0 = tmem_base, tO0 = tmem_base + 256;
-      auto dp = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
-      auto issue_qk = [&](int t, int sk) {
-        const uint32_t a_lo = q_lo + t * (A_TILE_BYTES >> 4), b_lo = k_lo + sk * (A_TILE_BYTES >> 4);
-#pragma unroll
-        for (int kk = 0; kk < A_D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * (A_HALF_BYTES >> 4) + (kk & 3) * 2;
-          umma_ss(tS0 + t * 128, dp(a_lo + off, HI), dp(b_lo + off, HI), idesc_qk, kk != 0);
-        }
-      };
-      auto issue_pv_tile = [&](int t, int sv, int j, bool leader) {
-        const uint32_t b_lo = v_lo + sv * (A_TILE_BYTES >> 4);
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          mbar_wait(&p_ready[2 * t + sl], j & 1);
-          tc_fence_after();
-          if (leader) {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const int kk = sl * 4 + k4;
-              umma_ts(tO0 + t * 128, tS0 + t * 128 + kk * 8, dp(b_lo + kk * (2048 >> 4), HI), idesc_pv,
-                      !(j == 0 && kk == 0));
-            }
-          }
-          __syncwarp();
-        }
-      };
-      const bool leader = elect_one();
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (leader) {
-        issue_qk(0, 0);
-        umma_commit(&s_full[0]);
-        issue_qk(1, 0);
-        umma_commit(&s_full[1]);
-        umma_commit(&k_empty[0]);
-      }
-      __syncwarp();
-      for (int j = 0; j < n_kv; ++j) {
-        const int sv = j % A_VS;
-        const bool last = (j + 1 == n_kv);
-        const int sk = (j + 1) % A_KS;
-        mbar_wait(&v_full[sv], (j / A_VS) & 1);
-        issue_pv_tile(0, sv, j, leader);
-        if (!last) mbar_wait(&k_full[sk], ((j + 1) / A_KS) & 1);
-        tc_fence_after();
-        if (leader) {
-          if (last) {
-            umma_commit(&o_final[0]);
-          } else {
-            issue_qk(0, sk);
-            umma_commit(&s_full[0]);
-          }
-        }
-        __syncwarp();
-        issue_pv_tile(1, sv, j, leader);
-        if (leader) {
-          umma_commit(&v_empty[sv]);
-          if (last) {
-            umma_commit(&o_final[1]);
-          } else {
-            issue_qk(1, sk);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[sk]);
-          }
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    reg_inc<104>();
-    const int t = warp >> 3;                       // query tile
-    const int hf = (warp >> 2) & 1;                // key half of the 128-key step
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;              // row in tile == TMEM lane
-    const int pair_bar = 1 + t * 4 + quad;         // named barrier shared with the partner warp
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + t * 128;
-    const uint32_t tO = tmem_base + lane_base + 256 + t * 128 + hf * 64;
-    const float c = p.scale_log2;
-    float m_used = -INFINITY;
-    float l_sum = 0.f;
-
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t s[64];
-      tmem_ld32(tS + hf * 64, s);
-      tmem_ld32(tS + hf * 64 + 32, s + 32);
-      tmem_ld_wait();
-      reg_fence32(s);
-      reg_fence32(s + 32);
-      const int valid = kv_len - j * A_BKV - hf * 64;      // keys of this half that exist
-      if (valid < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= valid) s[i] = 0xFF800000u;              // -inf
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int i = 4; i < 60; i += 8) {
-        mx0 = max3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-        mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-        mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-      }
-      mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
-      mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      // row max over both halves: exchange with the partner thread (same row, other key half).
-      // The barrier also orders the partner's tcgen05.ld of S before this thread's P store,
-      // which overwrites S columns the partner reads.
-      float* xs = xch + (((j & 1) * 2 + t) * 2) * 128;
-      xs[hf * 128 + row] = mx;
-      named_bar_sync(pair_bar, 64);
-      mx = fmaxf(mx, xs[(hf ^ 1) * 128 + row]);
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const float m_new = fmaxf(m_used, mx);
-        const bool grow = (m_new - m_used) * c > A_RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, grow)) {              // identical in the partner warp
-          const float f = grow ? fast_exp2((m_used - m_new) * c) : 1.0f;   // per-row, see the main kernel
-          if (grow) m_used = m_new;
-          l_sum *= f;
-#pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {                 // this half's 64 columns of O
-            uint32_t o[32];
-            tmem_ld32(tO + cc * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(tO + cc * 32, o);
-          }
-          tmem_st_wait();
-          named_bar_sync(pair_bar, 64);                    // both halves of O rescaled before any PV
-        }
-      }
-      const float neg_mc = -m_used * c;
-      float l0 = 0.f, l1 = 0.f;
-      uint32_t ph[32];
-      exp_pairs<0, 0, 32, 0>(s, ph, c, neg_mc, l0, l1);
-      tmem_st32(tS + hf * 32, ph);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[2 * t + hf]);
-      l_sum += l0 + l1;
-    }
-
-    // ---- epilogue: O / l -> bf16 -> global (this half's 64 channels)
-    float* ls = lxch + t * 2 * 128;
-    ls[hf * 128 + row] = l_sum;
-    named_bar_sync(pair_bar, 64);
-    l_sum += ls[(hf ^ 1) * 128 + row];
-    mbar_wait(&o_final[t], 0);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
-    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
-    const bool row_ok = q_row < p.Lq;
-    bf16* orow = p.out + static_cast<long long>(b) * p.out_stride_b +
-                 static_cast<long long>(q_row) * p.out_stride_l + head * A_D + hf * 64;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t o[32];
-      tmem_ld32(tO + cc * 32, o);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
-          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
-          if (p.accumulate) {
-            const uint4 prev = *dst;
-            const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
-              v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
-            }
-          }
-          uint4 ov;
-          ov.x = pack_bf16(v[0], v[1]);
-          ov.y = pack_bf16(v[2], v[3]);
-          ov.z = pack_bf16(v[4], v[5]);
-          ov.w = pack_bf16(v[6], v[7]);
-          *dst = ov;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 18) tmem_dealloc<512>(tmem_base);
-}
-
 }  // namespace m4d
 
 using namespace m4d;
@@ -1130,7 +632,6 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
                   aligned16(out),
               M4D_ERR_ALIGN);
 
-  const bool k64 = (g_debug_flags & 0x200) ? ((g_debug_flags & 0x400) != 0) : (A_DEFAULT_K64 != 0);
   CUtensorMap tmQ, tmK, tmV;
   auto mk = [&](CUtensorMap* m, const void* base, int L, long long sb, long long sl, uint32_t rows) {
     const uint32_t box[4] = {64, 1, rows, 1};
@@ -1141,44 +642,24 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
     return make_tmap_bf16(m, base, 4, dims, str, box);
   };
   int rc;
-  const uint32_t kv_rows = k64 ? B_BKV : A_BKV;
+  const uint32_t kv_rows = A_BKV;
   if ((rc = mk(&tmQ, q, Lq, q_stride_b, q_stride_l, A_BQ)) != M4D_OK) return rc;
   if ((rc = mk(&tmK, k, Lk, kv_stride_b, kv_stride_l, kv_rows)) != M4D_OK) return rc;
   if ((rc = mk(&tmV, v, Lk, kv_stride_b, kv_stride_l, kv_rows)) != M4D_OK) return rc;
 
-  // debug flags: 0x100 | (PP << 4) | VAR selects a measured variant; default = fastest measured
-  int pp = A_DEFAULT_PP, var = A_DEFAULT_VAR;
-  if (g_debug_flags & 0x100) {
-    pp = (g_debug_flags >> 4) & 0xF;
-    var = g_debug_flags & 0x7;
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = attn_fwd_d128_kernel<A_DEFAULT_PP, A_DEFAULT_MODE>;
+#ifdef M4D_DEV
+  // development build only: m4d_dev_set_flags(0x100 | (MODE << 4) | PP) selects a measured variant
+  if (g_dev_flags & 0x100) {
+    const int pp = g_dev_flags & 0xF, mode = (g_dev_flags >> 4) & 1;
+    kern = mode ? (pp == 0 ? attn_fwd_d128_kernel<0, 1> : pp == 1 ? attn_fwd_d128_kernel<1, 1>
+                   : pp == 2 ? attn_fwd_d128_kernel<2, 1> : attn_fwd_d128_kernel<3, 1>)
+                : (pp == 0 ? attn_fwd_d128_kernel<0, 0> : pp == 1 ? attn_fwd_d128_kernel<1, 0>
+                   : pp == 2 ? attn_fwd_d128_kernel<2, 0> : attn_fwd_d128_kernel<3, 0>);
   }
-  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = nullptr;
-  // debug flags 0x1000000 | (PACE << 20): pacing distance variant (0, 2, 4, 6)
-  int pace = A_DEFAULT_PACE;
-  if (g_debug_flags & 0x1000000) pace = (g_debug_flags >> 20) & 0xF;
-  if (pp == 0 && var == 0) {
-    kern = pace == 0 ? attn_fwd_d128_kernel<0, 0, 0>
-         : pace == 2 ? attn_fwd_d128_kernel<0, 0, 2>
-         : pace == 6 ? attn_fwd_d128_kernel<0, 0, 6> : attn_fwd_d128_kernel<0, 0, 4>;
-  } else if (pp == 0) {
-    kern = var == 1 ? attn_fwd_d128_kernel<0, 1, 0> : attn_fwd_d128_kernel<0, 2, 0>;
-  } else if (pp == 2) {
-    kern = (var & 1) ? attn_fwd_d128_kernel<2, 1, 0> : (pace ? attn_fwd_d128_kernel<2, 0, 4> : attn_fwd_d128_kernel<2, 0, 0>);
-  }
-  int smem_bytes = A_SMEM_BYTES;
-  int threads = A_THREADS;
-  if (k64) {
-    kern = attn_fwd_d128_k64_kernel;
-    smem_bytes = B_SMEM_BYTES;
-  }
-  // debug flags 0x4000000: explicit choice, bit 0x2000000 = split-softmax kernel
-  const bool split = (g_debug_flags & 0x4000000) ? ((g_debug_flags & 0x2000000) != 0) : (A_DEFAULT_SPLIT != 0);
-  if (split && !k64 && !(g_debug_flags & 0x100)) {
-    kern = attn_fwd_d128_split_kernel;
-    smem_bytes = C_SMEM_BYTES;
-    threads = C_THREADS;
-  }
-  if (kern == nullptr) return M4D_ERR_UNSUPPORTED;
+#endif
+  const int smem_bytes = A_SMEM_BYTES;
+  const int threads = A_THREADS;
   rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                "cudaFuncSetAttribute(attention)");
   if (rc != M4D_OK) return rc;
@@ -1193,12 +674,8 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
   p.scale_log2 = (softmax_scale > 0.f ? softmax_scale : 1.0f / sqrtf(static_cast<float>(A_D))) *
                  1.4426950408889634f;
   p.accumulate = accumulate;
-  p.flags = g_debug_flags;
   p.scatter_rows = n_scatter > 0 ? scatter_rows : 0;
   for (int i = 0; i < 8; ++i) p.out_scatter[i] = i < n_scatter ? static_cast<bf16*>(out_scatter[i]) : nullptr;
-  if (n_scatter > 0 && kern != static_cast<void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams)>(
-                                   attn_fwd_d128_kernel<0, 0, 0>))
-    return M4D_ERR_UNSUPPORTED;                 // the measured debug variants have no scatter epilogue
   dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
   kern<<<grid, threads, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
   M4D_CHECK_LAUNCH("attn_fwd_d128_kernel");

@@ -88,7 +88,11 @@ inline int sm_count() {
   return n;
 }
 
-extern int g_debug_flags;  // see m4d_set_debug_flags
+#ifdef M4D_DEV
+// Development builds only (`python more4d_b200/build.py -DM4D_DEV`): kernel-variant selection for
+// A/B measurements through m4d_dev_set_flags.  The product library has no global mutable state.
+extern int g_dev_flags;
+#endif
 
 // 2-CTA (cta_group::2) GEMM, gemm2.cu
 int gemm2_dispatch(const void* a, long long lda, const void* w, long long ldw, const void* bias, void* out,

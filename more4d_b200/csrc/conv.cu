@@ -190,58 +190,6 @@ conv_cl_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-// ---------------------------------------------------------------------------------------
-// Direct convolution for the 3-channel model inputs (Encoder3d.conv1 vae:289, adaptor conv_in
-// traj:142-146): K = 27*3 (or 9*3) is far too thin for tensor cores.  Input planar NCTHW bf16
-// (the module's own input layout, optionally with the `x*2-1` of infer_vae.py:278 fused),
-// output channels-last bf16.  One thread = one output pixel; weights staged in shared memory
-// as fp32.
-// ---------------------------------------------------------------------------------------
-template <int KT>
-__global__ void __launch_bounds__(128)
-conv_in3_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias,
-                bf16* __restrict__ out, int T, int H, int W, int Cout, float in_scale, float in_shift) {
-  extern __shared__ float wsm[];                 // [Cout][3*KT*9] + bias[Cout]
-  constexpr int KV = 3 * KT * 9;
-  for (int i = threadIdx.x; i < Cout * KV; i += blockDim.x) wsm[i] = __bfloat162float(w[i]);
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x)
-    wsm[Cout * KV + i] = bias ? __bfloat162float(bias[i]) : 0.f;
-  __syncthreads();
-  const int wq = blockIdx.x * blockDim.x + threadIdx.x;
-  const int h = blockIdx.y, t = blockIdx.z;
-  if (wq >= W) return;
-  const long long plane = static_cast<long long>(T) * H * W;
-  float xin[KV];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int a = 0; a < KT; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int tt = t + a - (KT - 1), hh = h + b - 1, ww = wq + d - 1;
-          float v = 0.f;
-          if (tt >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W) {
-            v = __bfloat162float(x[c * plane + (static_cast<long long>(tt) * H + hh) * W + ww]);
-            v = bf16_round(bf16_round(v * in_scale) + in_shift);
-          }
-          xin[((c * KT + a) * 3 + b) * 3 + d] = v;
-        }
-  bf16* o = out + ((static_cast<long long>(t) * H + h) * W + wq) * Cout;
-  for (int n = 0; n < Cout; n += 2) {
-    float a0 = wsm[Cout * KV + n], a1 = wsm[Cout * KV + n + 1];
-    const float* w0 = wsm + n * KV;
-    const float* w1 = w0 + KV;
-#pragma unroll
-    for (int k = 0; k < KV; ++k) {
-      a0 = fmaf(xin[k], w0[k], a0);
-      a1 = fmaf(xin[k], w1[k], a1);
-    }
-    *reinterpret_cast<uint32_t*>(o + n) = pack_bf16(a0, a1);
-  }
-}
-
 }  // namespace m4d
 
 using namespace m4d;
@@ -296,8 +244,12 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
                  ? 1 : 0;
 
   // 3x3 (x kt) stride-1 convolutions — almost all of the VAE's FLOPs — take the halo-staging
-  // kernel (conv_halo.cu); debug flag 0x10000 forces the per-tap kernel below.
-  if (!(g_debug_flags & 0x10000) &&
+  // kernel (conv_halo.cu); development builds: flag 0x10000 forces the per-tap kernel below.
+  bool use_halo = true;
+#ifdef M4D_DEV
+  use_halo = !(g_dev_flags & 0x10000);
+#endif
+  if (use_halo &&
       conv_halo_eligible(Cin, kt, kh, kw, st, sh, sw, pt, ph, pw, T_in, H_in, W_in, T_out, H_out, W_out))
     return conv_halo_launch(x, T_in, H_in, W_in, w_packed, Cout_pad, p, stream);
   M4D_REQUIRE(norm_out == nullptr, M4D_ERR_UNSUPPORTED);      // the fused norm lives in conv_halo.cu
@@ -371,34 +323,4 @@ extern "C" int m4d_conv3x3_rmsnorm_cl(const void* x, int T, int H, int W, int Ci
   M4D_REQUIRE(Cout == 96 || Cout == 192, M4D_ERR_UNSUPPORTED);
   return conv_cl_impl(x, T, H, W, Cin, w_packed, Cout, Cout, bias, kt, 3, 3, 1, 1, 1, kt - 1, 1, 1, T, H, W,
                       out, Cout, 1, 0, Cout, residual, 0, 0, nullptr, gamma, norm_out, do_silu, stream_);
-}
-
-extern "C" int m4d_conv_in3(const void* x, const void* w, const void* bias, void* out, int T, int H,
-                            int W, int Cout, int kt, float in_scale, float in_shift, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  M4D_REQUIRE(x && w && out && T > 0 && H > 0 && W > 0, M4D_ERR_BAD_SHAPE);
-  M4D_REQUIRE((kt == 1 || kt == 3) && Cout > 0 && Cout % 2 == 0, M4D_ERR_UNSUPPORTED);
-  M4D_REQUIRE(H <= 65535 && T <= 65535, M4D_ERR_BAD_SHAPE);
-  const int smem = (Cout * 3 * kt * 9 + Cout) * 4;
-  dim3 grid((W + 127) / 128, H, T);
-  if (kt == 3) {
-    static bool cfgd = false;
-    if (!cfgd) {
-      int rc = cuda_ok(cudaFuncSetAttribute(conv_in3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            96 * 1024), "cudaFuncSetAttribute(conv_in3)");
-      if (rc != M4D_OK) return rc;
-      cfgd = true;
-    }
-    M4D_REQUIRE(smem <= 96 * 1024, M4D_ERR_UNSUPPORTED);
-    conv_in3_kernel<3><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(w),
-                                                    static_cast<const bf16*>(bias), static_cast<bf16*>(out),
-                                                    T, H, W, Cout, in_scale, in_shift);
-  } else {
-    M4D_REQUIRE(smem <= 48 * 1024, M4D_ERR_UNSUPPORTED);
-    conv_in3_kernel<1><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(w),
-                                                    static_cast<const bf16*>(bias), static_cast<bf16*>(out),
-                                                    T, H, W, Cout, in_scale, in_shift);
-  }
-  M4D_CHECK_LAUNCH("conv_in3_kernel");
-  return M4D_OK;
 }

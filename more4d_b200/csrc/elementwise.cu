@@ -372,7 +372,9 @@ __global__ void silu_bf16_kernel(const float* __restrict__ x, bf16* __restrict__
   store4(out + idx * 4, v);
 }
 
-int g_debug_flags = 0;
+#ifdef M4D_DEV
+int g_dev_flags = 0;
+#endif
 
 }  // namespace m4d
 
@@ -616,7 +618,9 @@ extern "C" int m4d_silu_bf16(const float* x, void* out, long long n, void* strea
   return M4D_OK;
 }
 
-extern "C" void m4d_set_debug_flags(int flags) { g_debug_flags = flags; }
+#ifdef M4D_DEV
+extern "C" void m4d_dev_set_flags(int flags) { g_dev_flags = flags; }
+#endif
 
 extern "C" int m4d_version(void) { return 100; }
 

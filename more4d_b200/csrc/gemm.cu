@@ -28,7 +28,6 @@ constexpr int G_A_BYTES = GM * GK * 2;            // 16 KB
 constexpr int G_B_BYTES = GN * GK * 2;            // 32 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_SMEM_BYTES = GSTAGES * G_STAGE_BYTES + 256 + 1024;  // + barriers + align slack
-constexpr int G_DEFAULT_2CTA = 1;           // 1: route large GEMMs to the cta_group::2 kernel (gemm2.cu)
 constexpr int G_THREADS = 384;               // 4 control warps + 2 epilogue warpgroups
 
 struct GemmEpi {
@@ -332,11 +331,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   // panel width: weight slab of a panel <= ~48 MB, panels of (nearly) equal width
   const int num_n = (N + GN - 1) / GN;
   const long long slab = static_cast<long long>(GN) * K * 2;
-  static long long budget = 0;
-  if (budget == 0) {
-    const char* e = getenv("M4D_GEMM_PANEL_MB");   // development knob
-    budget = (e ? atoll(e) : 48) << 20;
-  }
+  constexpr long long budget = 48ll << 20;        // 32 / 48 / 72 MB measured within noise (profiles/gemm_r01.md)
   int pw_max = static_cast<int>(budget / (slab > 0 ? slab : 1));
   if (pw_max < 1) pw_max = 1;
   const int panels = (num_n + pw_max - 1) / pw_max;
@@ -373,10 +368,14 @@ extern "C" int m4d_gemm_bf16(const void* a, long long lda, const void* w, long l
   if (epilogue == M4D_EPI_ADD_BF16) M4D_REQUIRE(residual != nullptr && ldr >= N, M4D_ERR_BAD_SHAPE);
   if (bias) M4D_REQUIRE(aligned16(bias), M4D_ERR_ALIGN);
 
-  // 2-CTA kernel (gemm2.cu) for the large-M block GEMMs; debug flag 0x1000 forces it on,
-  // 0x2000 forces it off, otherwise G_DEFAULT_2CTA decides.
+  // 2-CTA kernel (gemm2.cu) for the large-M block GEMMs (development builds: flag 0x2000 forces
+  // the 1-CTA kernel for A/B timing).
   {
-    const bool want = (g_debug_flags & 0x2000) ? false : ((g_debug_flags & 0x1000) ? true : (G_DEFAULT_2CTA != 0));
+#ifdef M4D_DEV
+    const bool want = !(g_dev_flags & 0x2000);
+#else
+    const bool want = true;
+#endif
     const bool has = epilogue == M4D_EPI_BF16 || epilogue == M4D_EPI_GELU_TANH ||
                      epilogue == M4D_EPI_GATE_RESIDUAL_F32;
     if (want && has && M >= 1024 && N >= 256)

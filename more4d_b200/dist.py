@@ -44,24 +44,20 @@ def shard_indices(num_samples: int, rank: Optional[int] = None, world_size: Opti
 
 def gather_latents(local: Sequence[Tensor], num_samples: int, group=None) -> List[Tensor]:
     """All-gather per-sample latents (same shape everywhere) produced under `shard_indices`;
-    returns the full list in sample order on every rank."""
+    returns the full list in sample order on every rank.  Every rank must own at least one sample
+    (num_samples >= world size) — checked on every rank BEFORE any collective, so a mis-sized call
+    raises everywhere instead of hanging in NCCL."""
     rank, w = world()
     if w == 1:
         return list(local)
+    if num_samples < w:
+        raise RuntimeError(f"gather_latents: {num_samples} samples cannot be sharded over {w} ranks "
+                           "(every rank needs at least one sample)")
+    if len(local) != len(shard_indices(num_samples, rank, w)):
+        raise RuntimeError("gather_latents: `local` does not match this rank's shard")
     per_rank = (num_samples + w - 1) // w
-    ref = local[0] if len(local) else None
-    shape = torch.tensor(list(ref.shape) if ref is not None else [0] * 8, dtype=torch.int64)
-    # every rank needs the sample shape even if it owns nothing
-    shapes = [torch.zeros_like(shape) for _ in range(w)]
-    if ref is not None and ref.is_cuda:
-        shape = shape.to(ref.device)
-        shapes = [s.to(ref.device) for s in shapes]
-    dist.all_gather(shapes, shape, group=group)
-    full = next(s for s in shapes if int(s.sum()) > 0).tolist()
-    like = ref if ref is not None else None
-    if like is None:
-        raise RuntimeError("gather_latents: a rank without samples needs dtype/device; pass >= world_size samples")
-    buf = torch.zeros(per_rank, *full[:like.dim()], dtype=like.dtype, device=like.device)
+    like = local[0]
+    buf = torch.zeros(per_rank, *like.shape, dtype=like.dtype, device=like.device)
     for i, t in enumerate(local):
         buf[i].copy_(t)
     out = [torch.empty_like(buf) for _ in range(w)]

@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .cache_utils import teacache_decide, teacache_step_done
 from .config import DiTConfig
 
 Tensor = torch.Tensor
@@ -355,7 +356,8 @@ class WanAttentionBlock(nn.Module):
             self.spatial_guidance_self = self.spatial_guidance_ffn = None
 
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens=None, dtype=BF16,
-                t=0, dino_features=None, use_cls_token=False, cross_kv=None, sp=None):
+                t=0, dino_features=None, use_cls_token=False, cross_kv=None, sp=None,
+                guidance_silu=None):
         """x: [B, L, C] fp32 (bf16 accepted and widened); e: [B, 6, C] fp32.  Returns the fp32
         residual stream.  A contiguous fp32 `x` is updated in place and returned."""
         _no_grad_only("WanAttentionBlock")
@@ -372,8 +374,8 @@ class WanAttentionBlock(nn.Module):
         k_lens = torch.as_tensor(seq_lens).to(device=dev, dtype=torch.int32)
         context = None if context is None else context.to(BF16)
 
-        feats = None
-        if dino_features is not None and dino_features[0] is not None and \
+        feats = guidance_silu        # bf16 SiLU(features), hoisted by the model (identical for all blocks)
+        if feats is None and dino_features is not None and dino_features[0] is not None and \
                 self.spatial_guidance_self is not None:
             f, cls = dino_features
             src = cls.expand(-1, f.size(1), -1) if (use_cls_token and cls is not None) else f
@@ -516,6 +518,17 @@ class WanTransformer4DModel(nn.Module):
         if model_type == "i2v":
             self.img_emb = MLPProj(1280, dim, device=device)
         self.ref_conv = _Param((dim, in_dim_ref_conv, ph, pw), device=device) if add_ref_conv else None
+        # Motion-Perception front end (t4d:883-892): the frozen OmniMAE trunk is out of scope — any
+        # module with `.trunk.forward_patch_features(img, None) -> ([1, 196, 768], cls)` can be
+        # attached as `omnimae_extractor` (install() attaches the reference's own); the trainable
+        # feature_adapter, the bilinear resize and the temporal repeat run on the kernels here.
+        self.use_omnimae_guidance = bool(use_omnimae_guidance)
+        self.omnimae_extractor = None
+        self.dino_dim = 768
+        if use_omnimae_guidance:
+            self.feature_adapter = _seq(_Param((768, 768, 3, 3), device=device), _Slot(),
+                                        _Param((768, 768, 3, 3), device=device))
+        self._adapter_packed = {}
         self.control_adapter = None
         self.teacache = None
         self.cfg_skip_ratio = None
@@ -531,8 +544,8 @@ class WanTransformer4DModel(nn.Module):
                    text_dim=cfg.text_dim, out_dim=cfg.out_dim, num_heads=cfg.num_heads,
                    num_layers=cfg.num_layers, qk_norm=cfg.qk_norm,
                    cross_attn_norm=cfg.cross_attn_norm, eps=cfg.eps, add_ref_conv=cfg.add_ref_conv,
-                   in_dim_ref_conv=cfg.in_dim_ref_conv,
-                   use_spatial_guidance=cfg.use_spatial_guidance, device=device)
+                   in_dim_ref_conv=cfg.in_dim_ref_conv, use_omnimae_guidance=cfg.use_omnimae_guidance,
+                   use_spatial_guidance=cfg.use_spatial_guidance or cfg.use_omnimae_guidance, device=device)
 
     @classmethod
     def from_pretrained(cls, pretrained_model_path, subfolder=None, transformer_additional_kwargs=None,
@@ -686,9 +699,8 @@ class WanTransformer4DModel(nn.Module):
         _no_grad_only("WanTransformer4DModel")
         if subject_ref is not None or y_camera is not None:
             raise NotImplementedError("subject_ref / y_camera are not used by the 4D-STraG path")
-        if first_frame is not None:
-            raise NotImplementedError("first_frame requires the OmniMAE trunk (out of scope); "
-                                      "pass guidance_features instead")
+        if first_frame is not None and guidance_features is not None:
+            raise ValueError("pass either first_frame or guidance_features, not both")
         # @cfg_skip() wrapper semantics (cfg_optimization.py:5-39)
         bs = len(x)
         skip = (bs >= 2 and self.cfg_skip_ratio is not None and
@@ -701,14 +713,52 @@ class WanTransformer4DModel(nn.Module):
             clip_fea = None if clip_fea is None else clip_fea[h:]
             y = None if y is None else y[h:]
             full_ref = None if full_ref is None else full_ref[h:]
+            # the reference's wrapper slices EVERY tensor / tuple kwarg (cfg_optimization.py:18-25)
+            first_frame = None if first_frame is None else first_frame[h:]
+            if guidance_features is not None:
+                guidance_features = tuple(None if g is None else g[h:] for g in guidance_features)
         out = self._forward(x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag,
-                            conditioning)
+                            conditioning, first_frame)
         if skip:
             out = torch.cat([out, out], dim=0)
         return out
 
+    def motion_perception_features(self, first_frame: Tensor, target_hw, latent_T: int):
+        """t4d:1127-1156: first_frame [B, 3, H, W] in [0, 1] -> ((features [B, T*h*w, 768] bf16,
+        cls [B, 1, 768]), bf16 SiLU(features)).  ImageNet normalisation + the frozen OmniMAE trunk
+        run as the attached torch module (once per forward, out of scope); feature_adapter
+        (im2col + tcgen05 GEMM, SiLU fused into the second gather), bilinear resize and the
+        temporal repeat are kernels."""
+        if not self.use_omnimae_guidance or self.omnimae_extractor is None:
+            raise RuntimeError("first_frame needs use_omnimae_guidance=True and an attached "
+                               "`omnimae_extractor` (the OmniMAE trunk is not part of more4d_b200)")
+        dev = self.patch_embedding.weight.device
+        ff = first_frame.to(dev)
+        mean = torch.tensor([0.485, 0.456, 0.406], device=dev, dtype=ff.dtype).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225], device=dev, dtype=ff.dtype).view(1, 3, 1, 1)
+        ff = (ff - mean) / std                                            # transforms.Normalize, t4d:1134-1135
+        feats, cls = [], []
+        for i in range(ff.shape[0]):                                      # per-sample, like t4d:1138-1145
+            f, c = self.omnimae_extractor.trunk.forward_patch_features(ff[i:i + 1], None)
+            feats.append(f)
+            cls.append(c)
+        feats, cls = torch.cat(feats), torch.cat(cls)
+        B = ff.shape[0]
+        tok = feats.reshape(B, 14, 14, self.dino_dim).to(BF16).contiguous()   # channels-last already
+        fa = self.feature_adapter
+        h = tok
+        for idx, silu in ((0, False), (2, True)):
+            w = fa[idx].weight
+            key = (idx, w.data_ptr(), w._version)
+            if self._adapter_packed.get(idx, (None,))[0] != key:
+                self._adapter_packed[idx] = (key, ops.pack_conv_weight(w))
+            rows = ops.im2col3x3_cl(h, silu=silu)
+            h = ops.linear(rows, self._adapter_packed[idx][1], fa[idx].bias).view(B, 14, 14, self.dino_dim)
+        raw, act = ops.bilinear_repeat_cl(h, latent_T, int(target_hw[0]), int(target_hw[1]))
+        return (raw, cls.reshape(B, 1, self.dino_dim)), act
+
     def _forward(self, x, t, context, seq_len, clip_fea, y, full_ref, guidance_features, cond_flag=True,
-                 conditioning=None):
+                 conditioning=None, first_frame=None):
         dev = self.patch_embedding.weight.device
         if isinstance(x, (list, tuple)):
             x = torch.stack(list(x))
@@ -750,6 +800,11 @@ class WanTransformer4DModel(nn.Module):
             ctx = self.embed_context([c.to(device=dev, dtype=BF16) for c in context], clip_fea)
         seq_lens = torch.full((B,), n_tok, device=dev, dtype=torch.int32)
         grid_sizes = torch.tensor([grid] * B, device=dev, dtype=torch.int32)
+        guidance_silu = None
+        if first_frame is not None:                                # t4d:1127-1156
+            guidance_features, guidance_silu = self.motion_perception_features(first_frame, grid[1:], T)
+            if self.use_cls_token:
+                guidance_silu = None                               # blocks then project the CLS token instead
         sp = self.sp if self.sp_world_size > 1 else None
         if sp is not None:                                         # context parallel, t4d:1187-1198
             if guidance_features is not None:
@@ -758,7 +813,7 @@ class WanTransformer4DModel(nn.Module):
         run_blocks = True
         tc = self.teacache
         if tc is not None:                                         # t4d:1200-1270
-            run_blocks = tc.decide(e0, cond_flag)
+            run_blocks = teacache_decide(tc, e0, cond_flag)
             if not run_blocks:
                 prev = tc.previous_residual_cond if cond_flag else tc.previous_residual_uncond
                 xs = xs + prev.to(xs.device)[-xs.size(0):]         # cache hit: block stack skipped
@@ -768,7 +823,8 @@ class WanTransformer4DModel(nn.Module):
             for i, blk in enumerate(self.blocks):
                 xs = blk(xs, e0, seq_lens, grid_sizes, self.freqs, ctx, None, BF16, t,
                          dino_features=guidance_features, use_cls_token=self.use_cls_token,
-                         cross_kv=None if conditioning is None else conditioning.cross_kv[i], sp=sp)
+                         cross_kv=None if conditioning is None else conditioning.cross_kv[i], sp=sp,
+                         guidance_silu=guidance_silu)
             if tc is not None:
                 res = (xs.cpu() - ori) if tc.offload else (xs - ori)
                 if cond_flag:
@@ -780,7 +836,7 @@ class WanTransformer4DModel(nn.Module):
             tok = sp.gather_tokens(tok)                            # t4d:1320-1321
         out = ops.unpatchify(tok, ref_len, self.out_dim, T, H, W)
         if tc is not None:
-            tc.step_done(cond_flag)
+            teacache_step_done(tc, cond_flag)
         return out
 
 

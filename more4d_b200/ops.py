@@ -194,6 +194,10 @@ def layernorm_modulate(x: Tensor, weight: Optional[Tensor] = None, bias: Optiona
     if guidance is not None:
         _req(guidance, BF16, "guidance")
         guidance = guidance.contiguous()
+        n_batches = rows // (rows_per_batch or rows)
+        if guidance.dim() != 3 or guidance.shape[0] != n_batches or guidance.shape[2] != 2 * C:
+            raise ValueError(f"more4d_b200.layernorm_modulate: guidance must be [{n_batches}, rows, {2 * C}] "
+                             f"(one slab per batch element), got {tuple(guidance.shape)}")
         sg_rows = guidance.shape[1]
         sg_stride = guidance.stride(0)
     rc = _lib.lib().m4d_layernorm_modulate(
@@ -352,6 +356,35 @@ def silu_bf16(x: Tensor) -> Tensor:
     return out
 
 
+def im2col3x3_cl(x: Tensor, silu: bool = False) -> Tensor:
+    """x [F, H, W, C] bf16 channels-last -> im2col rows [F*H*W, 9*C] of a 3x3 / padding-1
+    convolution (tap-major, matching `pack_conv_weight`), optionally of SiLU(x)."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    if not x.is_contiguous() or x.dim() != 4:
+        raise ValueError("more4d_b200.im2col3x3_cl: x must be contiguous [F, H, W, C]")
+    F_, H, W, C = x.shape
+    rows = torch.empty(F_ * H * W, 9 * C, device=x.device, dtype=BF16)
+    rc = _lib.lib().m4d_im2col3x3_cl(x.data_ptr(), rows.data_ptr(), F_, H, W, C, int(silu), _stream())
+    _lib.check(rc, "m4d_im2col3x3_cl")
+    return rows
+
+
+def bilinear_repeat_cl(x: Tensor, T: int, H: int, W: int, want_raw: bool = True, want_silu: bool = True):
+    """x [B, h, w, C] bf16 -> bilinear (align_corners=False) resize to (H, W), repeated over T
+    frames: returns (raw, silu), each [B, T*H*W, C] bf16 or None."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    if not x.is_contiguous() or x.dim() != 4:
+        raise ValueError("more4d_b200.bilinear_repeat_cl: x must be contiguous [B, h, w, C]")
+    B, h, w, C = x.shape
+    raw = torch.empty(B, T * H * W, C, device=x.device, dtype=BF16) if want_raw else None
+    act = torch.empty(B, T * H * W, C, device=x.device, dtype=BF16) if want_silu else None
+    rc = _lib.lib().m4d_bilinear_repeat_cl(x.data_ptr(), _ptr(raw), _ptr(act), B, h, w, C, T, H, W, _stream())
+    _lib.check(rc, "m4d_bilinear_repeat_cl")
+    return raw, act
+
+
 # ======================================================================================
 # Motion-Sensitive VAE ops (channels-last bf16 activations [T, H, W, C])
 # ======================================================================================
@@ -433,21 +466,6 @@ def conv3x3_rmsnorm_cl(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout
 
 
 FUSED_NORM_CHANNELS = (96, 192)     # Cout values m4d_conv3x3_rmsnorm_cl supports
-
-
-def conv_in3(x_planar: Tensor, w: Tensor, bias: Optional[Tensor], kt: int, in_scale: float = 1.0,
-             in_shift: float = 0.0) -> Tensor:
-    """x [3, T, H, W] planar bf16 -> channels-last [T, H, W, Cout] (causal in time for kt = 3)."""
-    _lib.require_device()
-    _req(x_planar, BF16, "x")
-    x_planar = x_planar.contiguous()
-    _, T, H, W = x_planar.shape
-    cout = w.shape[0]
-    out = torch.empty(T, H, W, cout, device=x_planar.device, dtype=BF16)
-    rc = _lib.lib().m4d_conv_in3(x_planar.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), T, H, W,
-                                 cout, kt, in_scale, in_shift, _stream())
-    _lib.check(rc, "m4d_conv_in3")
-    return out
 
 
 def rmsnorm_silu_cl(x: Tensor, gamma: Tensor, silu: bool = True, inplace: bool = False) -> Tensor:

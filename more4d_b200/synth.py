@@ -93,6 +93,11 @@ def dit_param_specs(cfg: DiTConfig) -> Iterator[Tuple[str, tuple, float, float]]
     if cfg.add_ref_conv:
         yield "ref_conv.weight", (C, cfg.in_dim_ref_conv, ph, pw), 0.05, 0.0
         yield "ref_conv.bias", (C,), w, 0.0
+    if cfg.use_omnimae_guidance:
+        G = cfg.guidance_dim
+        for i in (0, 2):
+            yield f"feature_adapter.{i}.weight", (G, G, 3, 3), (9 * G) ** -0.5, 0.0
+            yield f"feature_adapter.{i}.bias", (G,), 0.1, 0.0
 
 
 def dit_state_dict(cfg: DiTConfig, seed: int = 0, device="cpu", dtype=torch.bfloat16,

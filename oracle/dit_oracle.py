@@ -214,6 +214,27 @@ def spatial_guidance(x: Tensor, feats: Tensor, cls: Optional[Tensor], sd, p: str
     return x * ar.r(1 + ar.r(scale * gate)) + ar.r(shift * gate)
 
 
+def mpm_front_end(tokens: Tensor, cls: Tensor, sd, target_hw: Tuple[int, int], latent_T: int,
+                  ar: Arith, return_adapter: bool = False):
+    """The Motion-Perception front end between the (out-of-scope) OmniMAE trunk and the blocks,
+    t4d:1146-1152: tokens [B, 196, 768] -> view [B, 768, 14, 14] -> feature_adapter
+    (Conv2d 3x3 -> SiLU -> Conv2d 3x3, t4d:888-892) -> F.interpolate(size, 'bilinear',
+    align_corners=False) -> repeat over latent_T -> [B, T*h*w, 768]; cls -> [B, 1, 768].
+    bf16 emulation rounds where the reference's bf16 tensors would (each conv / SiLU /
+    interpolate output)."""
+    B = tokens.shape[0]
+    G = tokens.shape[-1]
+    x = ar.r(tokens.float()).view(B, 14, 14, G).permute(0, 3, 1, 2)
+    x = ar.r(F.conv2d(x, sd["feature_adapter.0.weight"].float(), sd["feature_adapter.0.bias"].float(), padding=1))
+    x = ar.r(F.silu(x))
+    x = ar.r(F.conv2d(x, sd["feature_adapter.2.weight"].float(), sd["feature_adapter.2.bias"].float(), padding=1))
+    adapter = x
+    x = ar.r(F.interpolate(x, size=tuple(target_hw), mode="bilinear", align_corners=False))
+    x = x.unsqueeze(2).repeat(1, 1, latent_T, 1, 1).flatten(2).transpose(1, 2)
+    feats = (x.contiguous(), cls.float().view(B, 1, G))
+    return (feats, adapter) if return_adapter else feats
+
+
 # --------------------------------------------------------------------------------------
 # block / head / model
 # --------------------------------------------------------------------------------------

@@ -136,3 +136,163 @@ def load3d():
     load()
     return importlib.import_module("MoRe4D.models.wan_transformer3d")
 
+
+
+# --------------------------------------------------------------------------------------
+# The CALLER of the hot path: MoRe4D/pipeline/pipeline_wan_fun_control.py
+# --------------------------------------------------------------------------------------
+class EulerFlowScheduler:
+    """Stand-in for diffusers' FlowMatchEulerDiscreteScheduler (absent here; its sigma grid lives in
+    diffusers and is NOT guessed): the only in-tree schedule, get_sampling_sigmas
+    (MoRe4D/utils/fm_solvers.py:22-26), with the Euler update x += (sigma_next - sigma) * v in
+    fp32.  Interface = what pctl:576-577,741,825 uses: set_timesteps(n, device=, mu=), .timesteps,
+    .order, .step(model_output, t, sample, return_dict=False)."""
+    order = 1
+
+    def __init__(self, shift: float = 5.0):
+        self.shift = shift
+        self.timesteps = None
+        self.sigmas = None
+        self._i = 0
+
+    def set_timesteps(self, num_inference_steps, device=None, mu=None):
+        import numpy as np
+        sig = np.linspace(1, 0, num_inference_steps + 1)[:num_inference_steps]
+        sig = self.shift * sig / (1 + (self.shift - 1) * sig)
+        self.sigmas = np.append(sig, 0.0)
+        self.timesteps = torch.tensor(sig * 1000.0, dtype=torch.float32, device=device)
+        self._i = 0
+
+    def step(self, model_output, timestep, sample, return_dict=False):
+        dt = float(self.sigmas[self._i + 1] - self.sigmas[self._i])
+        self._i += 1
+        prev = (sample.float() + dt * model_output.float()).to(sample.dtype)
+        return (prev,)
+
+
+def _install_pipeline_stubs() -> None:
+    if "MoRe4D.pipeline.pipeline_wan_fun_control" in sys.modules:
+        return
+    import contextlib
+    import enum
+    from dataclasses import dataclass  # noqa: F401
+
+    class DiffusionPipeline:
+        """register_modules / components / progress_bar / maybe_free_model_hooks of diffusers'
+        base class, as pipeline_wan_fun_control.py:170-189,741,853 use them."""
+
+        def __init__(self):
+            self._components = {}
+
+        def register_modules(self, **kw):
+            for k, v in kw.items():
+                self._components[k] = v
+                setattr(self, k, v)
+
+        @property
+        def components(self):
+            return dict(self._components)
+
+        @contextlib.contextmanager
+        def progress_bar(self, total=None):
+            class _Bar:
+                def update(self, n=1):
+                    pass
+            yield _Bar()
+
+        def maybe_free_model_hooks(self):
+            pass
+
+    class _Proc:
+        def __init__(self, *a, **kw):
+            pass
+
+        def preprocess(self, x, height=None, width=None):
+            return x
+
+        def postprocess_video(self, video, output_type="np"):
+            return video
+
+    class BaseOutput:
+        pass
+
+    class KarrasDiffusionSchedulers(enum.Enum):
+        EulerDiscreteScheduler = 1
+
+    class SchedulerMixin:
+        pass
+
+    class SchedulerOutput:
+        def __init__(self, prev_sample):
+            self.prev_sample = prev_sample
+
+    def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+        return torch.randn(shape, generator=generator, dtype=dtype).to(device)
+
+    d = sys.modules["diffusers"]
+    d.FlowMatchEulerDiscreteScheduler = EulerFlowScheduler
+    _mod("diffusers.callbacks", MultiPipelineCallbacks=type("MultiPipelineCallbacks", (), {}),
+         PipelineCallback=type("PipelineCallback", (), {}))
+    _mod("diffusers.image_processor", VaeImageProcessor=_Proc)
+    _mod("diffusers.models.embeddings", get_1d_rotary_pos_embed=None)
+    _mod("diffusers.pipelines")
+    _mod("diffusers.pipelines.pipeline_utils", DiffusionPipeline=DiffusionPipeline)
+    _mod("diffusers.schedulers", FlowMatchEulerDiscreteScheduler=EulerFlowScheduler)
+    _mod("diffusers.schedulers.scheduling_utils", KarrasDiffusionSchedulers=KarrasDiffusionSchedulers,
+         SchedulerMixin=SchedulerMixin, SchedulerOutput=SchedulerOutput)
+    du = sys.modules["diffusers.utils"]
+    du.BaseOutput = BaseOutput
+    du.replace_example_docstring = lambda doc: (lambda f: f)
+    du.deprecate = lambda *a, **kw: None
+    du.is_scipy_available = lambda: True
+    _mod("diffusers.utils.torch_utils", randn_tensor=randn_tensor)
+    _mod("diffusers.video_processor", VideoProcessor=_Proc)
+    models = sys.modules["MoRe4D.models"]
+    models.AutoencoderKLWan = importlib.import_module("MoRe4D.models.wan_vae").AutoencoderKLWan
+    models.WanTransformer3DModel = importlib.import_module("MoRe4D.models.wan_transformer3d").WanTransformer3DModel
+    for name in ("AutoTokenizer", "CLIPModel", "WanT5EncoderModel"):
+        setattr(models, name, type(name, (), {}))
+    _mod("MoRe4D.pipeline").__path__ = [os.path.join(_PKG, "pipeline")]
+
+
+def load_pipeline():
+    """The reference's 4D-STraG pipeline module, imported in place with the stand-ins above; returns
+    (module, EulerFlowScheduler)."""
+    load()
+    _install_pipeline_stubs()
+    return importlib.import_module("MoRe4D.pipeline.pipeline_wan_fun_control"), EulerFlowScheduler
+
+
+# --------------------------------------------------------------------------------------
+# Motion-Perception front end (t4d:1127-1156): stand-in for the frozen OmniMAE ViT-B trunk
+# --------------------------------------------------------------------------------------
+class StubOmniMAE(nn.Module):
+    """Parameter-free stand-in for `vit_base_mae_pretraining()` (MoRe4D/models/omnimae.py:77-143;
+    the real one loads a checkpoint from a hard-coded path, omnimae.py:64-74).  The trunk is OUT OF
+    SCOPE — only its interface matters: `.trunk.forward_patch_features(img [1,3,H,W], None)` ->
+    (tokens [1, 196, 768], cls [1, 768]) (omnivision/models/vision_transformer.py:688-703).  Tokens
+    are a fixed deterministic function of the image so that the reference forward, the oracle and
+    the CUDA mirror see the same trunk output."""
+
+    class _Trunk(nn.Module):
+        def forward_patch_features(self, x, use_checkpoint=False):
+            import torch.nn.functional as F
+            g = torch.Generator().manual_seed(1234)
+            proj = torch.randn(3, 768, generator=g)
+            table = torch.randn(196, 768, generator=g) * 0.5
+            pooled = F.adaptive_avg_pool2d(x.float().cpu(), 14).flatten(2).transpose(1, 2)    # [1, 196, 3]
+            tok = (pooled @ proj + table).to(device=x.device)
+            return tok, tok.mean(dim=1)
+
+    def __init__(self):
+        super().__init__()
+        self.trunk = StubOmniMAE._Trunk()
+
+
+def load_with_stub_omnimae():
+    """load() with `MoRe4D.models.omnimae` pre-seeded by the stub, so that the REAL
+    WanTransformer4DModel(use_omnimae_guidance=True) constructs (t4d:883-892) and its REAL forward
+    runs the Motion-Perception branch (t4d:1127-1156) on CPU."""
+    mods = load()
+    _mod("MoRe4D.models.omnimae", vit_base_mae_pretraining=lambda pretrained=True: StubOmniMAE())
+    return mods

@@ -68,6 +68,36 @@ def block_case(t4d, name, cfg: DiTConfig, grid, seq_len, seed, guidance=False):
     print(name, tuple(y.shape), float(y.abs().mean()))
 
 
+def block14b_case(t4d, name="block_14b", seed=6):
+    """ONE block at the headline dims (Wan2.1-14B: C 5120, F 13824, 40 heads) and L = 1152 tokens
+    (grid 2x24x24: 9 key tiles, a 2-CTA GEMM M tail, K = 13 824 accumulation in ffn.2) through the
+    real WanAttentionBlock (t4d:585-688).  The full output is 23 MB in fp32, so 96 sampled rows are
+    stored, plus the increment y - x of the same rows (the residual pass-through masks errors in the
+    output-level number)."""
+    from more4d_b200.config import WAN_14B
+    cfg = WAN_14B.with_(num_layers=1)
+    C, grid, L = cfg.dim, (2, 24, 24), 1152
+    sd = synth.block_state_dict(cfg, 0, seed)
+    blk = t4d.WanAttentionBlock("i2v_cross_attn", C, cfg.ffn_dim, cfg.num_heads, (-1, -1), True, True, cfg.eps,
+                                use_spatial_guidance=False)
+    blk.load_state_dict(f32(sd), strict=True)
+    x = synth._randn(seed, "blk.x", (1, L, C), 1.0, "cpu", torch.bfloat16)
+    ctx = synth._randn(seed, "blk.ctx", (1, 257 + cfg.text_len, C), 1.0, "cpu", torch.bfloat16)
+    e0 = synth._randn(seed, "blk.e0", (1, 6, C), 0.3, "cpu", torch.float32)
+    d = cfg.head_dim
+    freqs = torch.cat([t4d.rope_params(1024, d - 4 * (d // 6)), t4d.rope_params(1024, 2 * (d // 6)),
+                       t4d.rope_params(1024, 2 * (d // 6))], dim=1)
+    y = blk(x.float(), e0, torch.tensor([L]), torch.tensor([list(grid)]), freqs, ctx.float(), None,
+            dtype=torch.float32, t=torch.tensor([500.0]))
+    rows = torch.arange(0, L, 12)                                   # 96 rows incl. both frames
+    out = {"rows": rows.to(torch.int32), "y_rows": y[0, rows].contiguous(),
+           "inc_rows": (y[0, rows] - x[0, rows].float()).contiguous(),
+           "y_sum": checksum(y), "x_sum": checksum(x), "ctx_sum": checksum(ctx), "e0_sum": checksum(e0),
+           "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))}
+    save_file(out, os.path.join(OUT, name + ".safetensors"))
+    print(name, tuple(y.shape), float(y.abs().mean()), float((y - x.float()).abs().mean()))
+
+
 def ops_case(t4d):
     """Leaf ops: rope_apply, WanRMSNorm, attention (SDPA branch)."""
     seed = 3
@@ -110,6 +140,34 @@ def model_case(t4d, name, cfg: DiTConfig, grid, batch, seed):
                "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))},
               os.path.join(OUT, name + ".safetensors"))
     print(name, tuple(y.shape), float(y.abs().mean()))
+
+
+def mpm_model_case(name="dit_tiny_mpm", seed=8):
+    """Full tiny model WITH the Motion-Perception front end: the real forward's first_frame branch
+    (t4d:1127-1156: ImageNet normalise -> OmniMAE trunk [stub, out of scope] -> feature_adapter ->
+    bilinear -> repeat over latent_T) feeding the real SpatialGuidanceModule in every block."""
+    t4d, _, _ = ref_import.load_with_stub_omnimae()
+    cfg = WAN_TINY.with_(use_spatial_guidance=True, use_omnimae_guidance=True)
+    grid, batch = (3, 4, 6), 2
+    sd = synth.dit_state_dict(cfg, seed)
+    m = t4d.WanTransformer4DModel(
+        model_type="i2v", in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim, num_heads=cfg.num_heads,
+        num_layers=cfg.num_layers, text_dim=cfg.text_dim, text_len=cfg.text_len, add_ref_conv=True,
+        use_dino_guidance=False, use_omnimae_guidance=True)
+    m.load_state_dict(f32(sd), strict=True)
+    m.eval()
+    inp = synth.dit_inputs(cfg, grid, batch, seed)
+    ff = synth._randn(seed, "in.first_frame", (batch, 3, 40, 56), 0.25, "cpu", torch.float32, mean=0.5).clamp(0, 1)
+    captured = {}
+    orig_adapter = m.feature_adapter.forward
+    m.feature_adapter.forward = lambda t: captured.setdefault("adapter_out", orig_adapter(t))
+    y = m(x=inp["x"].float(), t=inp["t"], context=[c.float() for c in inp["context"]], seq_len=inp["seq_len"],
+          clip_fea=inp["clip_fea"].float(), y=inp["y"].float(), full_ref=inp["full_ref"].float(), first_frame=ff)
+    save_file({"y": y.contiguous(), "adapter_out": captured["adapter_out"].contiguous(), "x_sum": checksum(inp["x"]),
+               "ff_sum": checksum(ff),
+               "w_sum": checksum(torch.cat([v.flatten().float() for v in sd.values()]))},
+              os.path.join(OUT, name + ".safetensors"))
+    print(name, tuple(y.shape), float(y.abs().mean()), tuple(captured["adapter_out"].shape))
 
 
 def model3d_case(t3d, name, cfg: DiTConfig, grid, batch, seed):
@@ -206,6 +264,12 @@ def vae_cases(vae_mod, traj_mod):
 
 def main():
     t4d, _vae, _traj = ref_import.load()
+    if "--only-14b" in sys.argv:
+        block14b_case(t4d)
+        return
+    if "--only-mpm" in sys.argv:
+        mpm_model_case()
+        return
     from more4d_b200.config import WAN_TINY_INP
     model3d_case(ref_import.load3d(), "dit3d_tiny", WAN_TINY_INP, (3, 4, 6), 2, seed=5)
     if "--only-3d" in sys.argv:

