@@ -34,14 +34,13 @@ constexpr int A_D = 128;
 constexpr int A_KS = 2, A_VS = 2;
 constexpr int A_TILE_BYTES = 128 * 128 * 2;   // 32 KB, stored as two [128 x 64] SW128 halves
 constexpr int A_HALF_BYTES = 128 * 64 * 2;    // 16 KB
-constexpr int A_THREADS = 384;
-constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024;
-#ifndef A_PIPE_D
-#define A_PIPE_D 3               // software-pipeline distance (pairs) between an EX2 and its consumers
-#endif
+constexpr int A_THREADS = 384;         // 8 softmax warps + TMA + MMA + TMEM allocator
+constexpr int A_THREADS_SPLIT = 608;   // MODE 2: 16 softmax warps (two per 32-row group) + the same three
+constexpr int A_XCHG_BYTES = 2 * 4 * 2 * 32 * 4;   // MODE 2: one float per (tile, row group, half, lane)
+constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024 + A_XCHG_BYTES;
 
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
-constexpr int A_DEFAULT_PP = 0;               // pairs (of 8) whose 2^x runs on the FMA pipe
+constexpr int A_DEFAULT_PP = 2;               // pairs (of 8) whose 2^x runs on the FMA pipe
 constexpr int A_DEFAULT_MODE = 1;             // 1: sum-guarded speculative reference
 constexpr float A_SUM_GUARD = 65536.0f;       // MODE 1: a half tile whose row sum reaches 2^16 moves the reference
 
@@ -68,23 +67,26 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
       : "+f"(d0), "+f"(d1)
       : "f"(a0), "f"(a1));
 }
-// 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split with a round-down
-// magic add, degree-3 minimax polynomial for 2^frac (rel. error ~1e-4, far below the bf16
-// rounding of P), exponent re-inserted with an integer add.  Offloads part of the softmax's
-// exponentials from the 16/clk/SM MUFU, which is otherwise co-critical with the tensor pipe
-// (128 keys x 256 rows = 2048 MUFU clocks per step and SM sub-partition = the step's MMA time).
-__device__ __forceinline__ void ex2_emul2(float x0, float x1, float& r0, float& r1) {
-  const float kMagic = 12582912.0f;              // 1.5 * 2^23
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  float t0, t1;
-  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t0) : "f"(x0), "f"(kMagic));
-  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t1) : "f"(x1), "f"(kMagic));
-  float b0 = t0, b1 = t1;
-  add2(b0, b1, -kMagic, -kMagic);                // floor(x)
-  float f0, f1;
-  fma2(f0, f1, b0, b1, -1.0f, -1.0f, x0, x1);    // frac = x - floor(x) in [0, 1)
-  float p0, p1;
+// 2^(s*c + neg_mc) for a pair on the FMA/ALU pipes instead of the MUFU.  The argument is clamped to
+// [-126, 128] inside the multiply-add that forms it: u = sat((x + 126) / 254) in [0, 1] comes out of
+// fma.rn.sat with pre-divided constants (cn = c / 254, bn = (neg_mc + 126) / 254), a round-down
+// fma against the magic number 1.5 * 2^23 splits x = u * 254 - 126 into floor and fraction, a
+// degree-3 minimax polynomial gives 2^frac (rel. error ~1e-4, far below the bf16 rounding of P) and
+// the exponent is re-inserted with one integer multiply-add.  Saturation matters: against a stale
+// reference x can be anything; x >= 128 must come out as +inf / huge (so that the row-sum guard
+// fires) and x <= -126 as ~0 — the unclamped integer exponent insert wraps around instead.
+// 11 instructions per pair; offloads the 16/clk/SM MUFU, which is otherwise co-critical with the
+// tensor pipe (128 keys x 256 rows = 2048 MUFU clocks per step and SM sub-partition = the MMA time).
+__device__ __forceinline__ void ex2_poly2(float s0, float s1, float cn, float bn, float& r0, float& r1) {
+  const float kM = 12582912.0f - 126.0f;         // 1.5 * 2^23 - 126
+  float u0, u1, t0, t1;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u0) : "f"(s0), "f"(cn), "f"(bn));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u1) : "f"(s1), "f"(cn), "f"(bn));
+  asm("fma.rm.ftz.f32 %0, %1, %2, %3;" : "=f"(t0) : "f"(u0), "f"(254.0f), "f"(kM));   // floor(x) + 1.5 * 2^23
+  asm("fma.rm.ftz.f32 %0, %1, %2, %3;" : "=f"(t1) : "f"(u1), "f"(254.0f), "f"(kM));
+  float g0, g1, f0, f1, p0, p1;
+  fma2(g0, g1, t0, t1, -1.0f, -1.0f, kM, kM);                      // -126 - floor(x), exact
+  fma2(f0, f1, u0, u1, 254.0f, 254.0f, g0, g1);                    // frac = x - floor(x) in [0, 1)
   fma2(p0, p1, f0, f1, 0.077119089663028717f, 0.077119089663028717f, 0.227564394474029541f,
        0.227564394474029541f);
   fma2(p0, p1, p0, p1, f0, f1, 0.695146143436431885f, 0.695146143436431885f);
@@ -93,34 +95,42 @@ __device__ __forceinline__ void ex2_emul2(float x0, float x1, float& r0, float& 
   r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-// p = 2^(s*c + neg_mc) for the logit pairs [Q0, Q0 + NQ) of a row (s = all 128 logits of the tile),
-// packed bf16x2 into pk[0 .. NQ); row-sum partials accumulate pairwise (FADD2) in pair order.
-// The consumers of pair q (FADD2 row sum, F2FP pack) are written A_PIPE_D pairs behind its two
-// EX2s: a warp issues in order, and consumers right behind their producers expose the MUFU
-// result latency on every pair (profiles/attn_r01c.md: 64 x [EX2, EX2, FADD2, F2FP] ran at ~20
-// instead of 16 clocks per pair).
-template <int PP, int Q0, int NQ>
+// Which logit pairs take the polynomial 2^x: PP of every 8, spread evenly so that the MUFU queue and
+// the FMA pipe stay busy side by side (PP >= 8: the contiguous tail pattern of round 1, PP - 8 of 8).
+template <int PP>
+__device__ __forceinline__ constexpr bool poly_pair(int q) {
+  return PP == 0 ? false
+       : PP == 1 ? (q & 7) == 7
+       : PP == 2 ? (q & 3) == 3
+       : PP == 3 ? ((q & 7) == 2 || (q & 7) == 5 || (q & 7) == 7)
+       : PP == 4 ? (q & 1) == 1
+       : (q & 7) >= 16 - PP;   // PP = 10: pairs 6, 7 of every 8
+}
+
+// p = 2^(s*c + neg_mc) for the logit pairs [Q0, Q0 + NQ) of s (KEY0/2 + q = pair index inside the
+// 128-key tile, which fixes the MUFU / polynomial assignment per key column), packed bf16x2 into
+// pk[0 .. NQ); row-sum partials accumulate pairwise (FADD2) in pair order.  The instruction order
+// is ptxas's: it interleaves ~4 FMA-pipe instructions per MUFU.EX2 and keeps the consumers of a
+// pair one pair behind its EX2s whatever order the source uses (measured on the SASS).
+template <int PP, int Q0, int NQ, int KEY0 = 0>
 __device__ __forceinline__ void exp_pipe(const uint32_t* s, uint32_t* pk, float c, float neg_mc,
                                          float& l0, float& l1) {
-  constexpr int D = A_PIPE_D;
-  float e0[NQ], e1[NQ];
+  const float cn = c * (1.0f / 254.0f), bn = (neg_mc + 126.0f) * (1.0f / 254.0f);
 #pragma unroll
-  for (int i = 0; i < NQ + D; ++i) {
-    if (i < NQ) {
-      const int q = Q0 + i;
+  for (int i = 0; i < NQ; ++i) {
+    const int q = Q0 + i;
+    const float s0 = __uint_as_float(s[2 * q]), s1 = __uint_as_float(s[2 * q + 1]);
+    float e0, e1;
+    if (PP != 0 && poly_pair<PP>(KEY0 / 2 + q)) {
+      ex2_poly2(s0, s1, cn, bn, e0, e1);
+    } else {
       float x0, x1;
-      fma2(x0, x1, __uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1]), c, c, neg_mc, neg_mc);
-      if ((q & 7) >= 8 - PP) {
-        ex2_emul2(x0, x1, e0[i], e1[i]);
-      } else {
-        e0[i] = fast_exp2(x0);
-        e1[i] = fast_exp2(x1);
-      }
+      fma2(x0, x1, s0, s1, c, c, neg_mc, neg_mc);
+      e0 = fast_exp2(x0);
+      e1 = fast_exp2(x1);
     }
-    if (i >= D) {
-      add2(l0, l1, e0[i - D], e1[i - D]);
-      pk[i - D] = pack_bf16(e0[i - D], e1[i - D]);
-    }
+    add2(l0, l1, e0, e1);
+    pk[i] = pack_bf16(e0, e1);
   }
 }
 
@@ -150,14 +160,14 @@ struct AttnParams {
   int scatter_rows;                       // 0 = plain output
 };
 
-// PP: pairs of every 8 whose exponential runs on the FMA pipe (ex2_emul2); MODE 0: exact row max
+// PP: pairs of every 8 whose exponential runs on the FMA pipe (ex2_poly2); MODE 0: exact row max
 // before the exponentials, MODE 1: sum-guarded speculative reference (see the softmax section).  P is handed to the tensor pipe in two 64-key halves.
 // Measured variants that did NOT help on the B200 and were removed again (round 1,
 // profiles/attn_variant_sweep_r01.log): one mbarrier arrival per warp instead of per thread
 // (-4 %), P in 1 or 4 slices, 64-key steps with a double-buffered S (-25 %: N=64 QK MMAs are
 // shared-memory bound), two threads per row (16 softmax warps share the MUFU: -9 %).
 template <int PP, int MODE>
-__global__ void __launch_bounds__(A_THREADS, 1)
+__global__ void __launch_bounds__(MODE == 2 ? A_THREADS_SPLIT : A_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -176,7 +186,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* p_ready = s_full + 2;       // per tile t: [4t + 0/1] P halves ready, [4t + 2] PV of the first half done
   uint64_t* o_final = p_ready + 8;      // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // MODE 2 partner exchange
 
+  constexpr int NSW = (MODE == 2) ? 16 : 8;       // softmax warps; then TMA, MMA, TMEM-allocator warps
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -189,12 +201,12 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (kv_len < 1) kv_len = 1;
   const int n_kv = (kv_len + A_BKV - 1) / A_BKV;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == NSW && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == NSW + 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < A_KS; ++s) {
       mbar_init(&k_full[s], 1);
@@ -211,16 +223,16 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     fence_mbar_init();
   }
-  if (warp == 10) tmem_alloc<512>(tmem_slot);
+  if (warp == NSW + 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
+  if (warp >= NSW) {
     // ------------------------------------------------------------------ data movement + MMA
-    reg_dec<80>();
-    if (warp == 8 && lane == 0) {
+    if (MODE != 2) reg_dec<80>();
+    if (warp == NSW && lane == 0) {
       mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
       for (int t = 0; t < A_NQ; ++t)
         for (int h = 0; h < 2; ++h)
@@ -239,7 +251,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tma_load_4d(sV + sv * A_TILE_BYTES + h * A_HALF_BYTES, &tmV, &v_full[sv], h * 64, head,
                       j * A_BKV, b);
       }
-    } else if (warp == 9) {
+    } else if (warp == NSW + 1) {
       // The whole warp runs this loop converged and ONE elected lane issues: operands then live
       // in uniform registers and every descriptor is {lo + compile-time offset, constant hi}.
       // With `if (lane == 0)` the compiler wraps each tcgen05.mma in an R2UR/ELECT loop and
@@ -331,6 +343,175 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         __syncwarp();
       }
     }
+  } else if (MODE == 2) {
+    // ------------------------------------------------------------------ softmax, split columns
+    // MODE 2.  With one warp per 32 rows the softmax of a tile is a single in-order instruction
+    // stream: ~560 instructions (MODE 1, PP 2) took ~1700 clocks against 768 clocks of MUFU work
+    // and 1024 clocks of MMA time per tile (profiles/attn_r02a.md: the softmax warps are busy 62 %
+    // of the step, the tensor pipe idles while both tiles are in their softmax).  Here TWO warps
+    // share a row group: warp (t, half 0, quad) owns key columns 0..63 of its 32 rows, warp
+    // (t, half 1, quad) columns 64..127 — two independent instruction streams per sub-partition
+    // and tile hide each other's latencies.  The sum-guarded reference of MODE 1 makes that cheap:
+    // no row max, hence no per-tile exchange between the partners; each half's row sum is the
+    // guard of that half and ONE named barrier with an OR-reduction (barrier.red.or) per tile tells
+    // both warps whether any of their 64 threads tripped it.  If so (always at j = 0, rarely
+    // later) both take the exact path together: publish the half-row maxima of the rows that
+    // tripped, move those rows' reference to the same value in both partners, rescale O (each
+    // warp its 64 output columns) / l, redo both halves from S (intact: the barrier precedes the
+    // P stores).  l is kept as two partial sums and combined once in the epilogue.
+    const int t = warp >> 3;                       // query tile
+    const int half = (warp >> 2) & 1;              // key-column half of the tile
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;              // row in tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tSh = tS + half * 64;           // my 64 logit columns
+    const uint32_t tPh = tS + half * 32;           // my 32 packed-P columns
+    const uint32_t tOh = tmem_base + lane_base + 256 + t * 128 + half * 64;   // my 64 output columns
+    const float c = p.scale_log2;
+    const int bar_id = 1 + t * 4 + quad;           // named barrier of the two partner warps
+    float* my_x = xchg + ((t * 4 + quad) * 2 + half) * 32 + lane;
+    float* partner_x = xchg + ((t * 4 + quad) * 2 + (half ^ 1)) * 32 + lane;
+    uint32_t pr;       // opaque to the compiler, otherwise it re-derives the address late (and the arrive with it)
+    asm volatile("mov.u32 %0, %1;" : "=r"(pr) : "r"(smem_u32(&p_ready[4 * t + half])));
+    float m_used = -INFINITY;                      // reference, in logit units; identical in both partners
+    float l_part = 0.f;                            // row sum over my key columns
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      uint32_t pk[32];
+      const int valid = kv_len - j * A_BKV - half * 64;      // keys of my half that exist (may be <= 0)
+      float l0 = 0.f, l1 = 0.f;
+      tmem_ld32(tSh, s);
+      tmem_ld_wait();                              // first 32 logits have landed
+      tmem_ld32(tSh + 32, s + 32);                 // in flight while they are processed
+      reg_fence32(s);
+      if (valid < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= valid) s[i] = 0xFF800000u;      // -inf
+      }
+      float neg_mc = -m_used * c;
+      if (half == 0) exp_pipe<PP, 0, 16, 0>(s, pk, c, neg_mc, l0, l1);
+      else           exp_pipe<PP, 0, 16, 64>(s, pk, c, neg_mc, l0, l1);
+      tmem_ld_wait();
+      reg_fence32(s + 32);
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 32; i < 64; ++i)
+          if (i >= valid) s[i] = 0xFF800000u;
+      }
+      if (half == 0) exp_pipe<PP, 16, 16, 0>(s, pk + 16, c, neg_mc, l0, l1);
+      else           exp_pipe<PP, 16, 16, 64>(s, pk + 16, c, neg_mc, l0, l1);
+      const bool tripped = (j == 0) || !(l0 + l1 < A_SUM_GUARD);   // j = 0: no reference yet
+      uint32_t any;
+      asm volatile("{\n\t.reg .pred pi, po;\n\t"
+                   "setp.ne.u32 pi, %1, 0;\n\t"
+                   "barrier.cta.red.or.pred po, %2, 64, pi;\n\t"
+                   "selp.u32 %0, 1, 0, po;\n\t}\n"
+                   : "=r"(any) : "r"(static_cast<uint32_t>(tripped)), "r"(bar_id) : "memory");
+      if (any) {
+        // exact path, both partner warps.  Nothing of this tile has been stored, so S is intact;
+        // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled.
+        float mxh = -INFINITY;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t o[32];
+          tmem_ld32(tSh + cc * 32, o);
+          tmem_ld_wait();
+          mxh = max32(o, valid - cc * 32, mxh);
+        }
+        *my_x = tripped ? mxh : -INFINITY;         // only rows that tripped THEMSELVES move (per-row decision)
+        named_bar_sync(bar_id, 64);
+        const float m_new = fmaxf(m_used, fmaxf(tripped ? mxh : -INFINITY, *partner_x));
+        const float f = (j == 0) ? 0.f : fast_exp2((m_used - m_new) * c);   // 1 for rows that did not move
+        m_used = m_new;
+        l_part *= f;
+        if (j > 0) {
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {         // my 64 output columns; every lane takes part
+            uint32_t o[32];
+            tmem_ld32(tOh + cc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tOh + cc * 32, o);
+          }
+          tmem_st_wait();
+        }
+        neg_mc = -m_used * c;
+        tmem_ld32(tSh, s);
+        tmem_ld32(tSh + 32, s + 32);
+        tmem_ld_wait();
+        reg_fence32(s);
+        reg_fence32(s + 32);
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) s[i] = 0xFF800000u;
+        }
+        l0 = 0.f;
+        l1 = 0.f;
+        if (half == 0) exp_pipe<PP, 0, 32, 0>(s, pk, c, neg_mc, l0, l1);
+        else           exp_pipe<PP, 0, 32, 64>(s, pk, c, neg_mc, l0, l1);
+        named_bar_sync(bar_id, 64);                // the partner has re-read its S columns: P may overwrite them
+      }
+      tmem_st32(tPh, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pr) : "memory");
+      l_part += l0 + l1;
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global, 64 output columns per warp
+    *my_x = l_part;
+    named_bar_sync(bar_id, 64);
+    const float inv_l = 1.0f / (half == 0 ? l_part + *partner_x : *partner_x + l_part);   // same order in both partners
+    mbar_wait(&o_final[t], 0);
+    tc_fence_after();
+    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
+    const bool row_ok = q_row < p.Lq;
+    bf16* obase = p.out;
+    int o_row = q_row;
+    if (p.scatter_rows > 0 && row_ok) {
+      const int dst = q_row / p.scatter_rows;
+      obase = p.out_scatter[dst];
+      o_row = q_row - dst * p.scatter_rows;
+    }
+    bf16* orow = obase + static_cast<long long>(b) * p.out_stride_b +
+                 static_cast<long long>(o_row) * p.out_stride_l + head * A_D + half * 64;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tOh + cc * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
+          if (p.accumulate) {
+            const uint4 prev = *dst;
+            const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
+              v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+          }
+          uint4 ov;
+          ov.x = pack_bf16(v[0], v[1]);
+          ov.y = pack_bf16(v[2], v[3]);
+          ov.z = pack_bf16(v[4], v[5]);
+          ov.w = pack_bf16(v[6], v[7]);
+          *dst = ov;
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
     // Per 128-key step and query tile the chain  S ready -> P ready -> PV -> QK(next) -> S ready
@@ -413,10 +594,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (i >= valid) s[i] = 0xFF800000u;
         }
         exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
-        if (__any_sync(0xffffffffu, !(l0 + l1 < A_SUM_GUARD))) {
+        if (__any_sync(0xffffffffu, (j == 0) || !(l0 + l1 < A_SUM_GUARD))) {
           // exact path for the whole tile: S is intact (nothing of this tile has been stored);
           // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled
-          const bool mine = !(l0 + l1 < A_SUM_GUARD);
+          const bool mine = (j == 0) || !(l0 + l1 < A_SUM_GUARD);
           float mxr = -INFINITY;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -599,7 +780,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) tmem_dealloc<512>(tmem_base);
+  if (warp == NSW + 2) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace m4d
@@ -648,18 +829,26 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
   if ((rc = mk(&tmV, v, Lk, kv_stride_b, kv_stride_l, kv_rows)) != M4D_OK) return rc;
 
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = attn_fwd_d128_kernel<A_DEFAULT_PP, A_DEFAULT_MODE>;
+  int threads = A_DEFAULT_MODE == 2 ? A_THREADS_SPLIT : A_THREADS;
 #ifdef M4D_DEV
   // development build only: m4d_dev_set_flags(0x100 | (MODE << 4) | PP) selects a measured variant
   if (g_dev_flags & 0x100) {
-    const int pp = g_dev_flags & 0xF, mode = (g_dev_flags >> 4) & 1;
-    kern = mode ? (pp == 0 ? attn_fwd_d128_kernel<0, 1> : pp == 1 ? attn_fwd_d128_kernel<1, 1>
-                   : pp == 2 ? attn_fwd_d128_kernel<2, 1> : attn_fwd_d128_kernel<3, 1>)
-                : (pp == 0 ? attn_fwd_d128_kernel<0, 0> : pp == 1 ? attn_fwd_d128_kernel<1, 0>
-                   : pp == 2 ? attn_fwd_d128_kernel<2, 0> : attn_fwd_d128_kernel<3, 0>);
+    const int pp = g_dev_flags & 0xF, mode = (g_dev_flags >> 4) & 3;
+    if (mode == 2) {
+      kern = pp == 0 ? attn_fwd_d128_kernel<0, 2> : pp == 1 ? attn_fwd_d128_kernel<1, 2>
+           : pp == 2 ? attn_fwd_d128_kernel<2, 2> : pp == 3 ? attn_fwd_d128_kernel<3, 2> : attn_fwd_d128_kernel<4, 2>;
+      threads = A_THREADS_SPLIT;
+    } else if (mode == 1) {
+      kern = pp == 0 ? attn_fwd_d128_kernel<0, 1> : pp == 1 ? attn_fwd_d128_kernel<1, 1>
+           : pp == 2 ? attn_fwd_d128_kernel<2, 1> : pp == 3 ? attn_fwd_d128_kernel<3, 1> : attn_fwd_d128_kernel<10, 1>;
+      threads = A_THREADS;
+    } else {
+      kern = pp == 0 ? attn_fwd_d128_kernel<0, 0> : attn_fwd_d128_kernel<2, 0>;
+      threads = A_THREADS;
+    }
   }
 #endif
   const int smem_bytes = A_SMEM_BYTES;
-  const int threads = A_THREADS;
   rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                "cudaFuncSetAttribute(attention)");
   if (rc != M4D_OK) return rc;

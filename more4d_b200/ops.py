@@ -24,14 +24,32 @@ def launches() -> int:
     return _Stats.launches
 
 
-def start_kernel_timing() -> None:
-    """Bracket every self-attention launch with CUDA events on the launching stream."""
-    _Stats.timed = {"attention": []}
+def start_kernel_timing(classes=("attention",)) -> None:
+    """Bracket the launches of the given kernel classes with CUDA events on the launching stream:
+    "attention" (self-attention, Lq == Lk), "cross_attention", "gemm", "rows" (LayerNorm / RMSNorm /
+    RoPE passes).  bench.py uses "attention" inside the timed region (40 launches per forward) and
+    all classes in a separate, untimed profiling pass."""
+    _Stats.timed = {c: [] for c in classes}
 
 
 def stop_kernel_timing():
     t, _Stats.timed = _Stats.timed, None
     return t
+
+
+def _t0(cls: str):
+    if _Stats.timed is None or cls not in _Stats.timed:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _t1(cls: str, ev0, work: float) -> None:
+    if ev0 is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        _Stats.timed[cls].append((ev0, ev1, work))
 
 
 def _stream() -> int:
@@ -93,12 +111,14 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, epilogue: i
         res2 = residual.reshape(-1, N)
     if bias is not None:
         _req(bias, BF16, "bias")
+    ev = _t0("gemm")
     rc = _lib.lib().m4d_gemm_bf16(
         x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
         out2.data_ptr(), out2.stride(0), M, N, K, epilogue,
         _ptr(res2), 0 if res2 is None else res2.stride(0), _ptr(gate), gate_batch_stride,
         rows_per_batch, _stream())
     _lib.check(rc, "m4d_gemm_bf16")
+    _t1("gemm", ev, 2.0 * M * N * K)
     return out
 
 
@@ -124,18 +144,14 @@ def attention(q: Tensor, k: Tensor, v: Tensor, k_lens: Optional[Tensor] = None,
     _req(out, BF16, "out")
     if k_lens is not None:
         _req(k_lens, torch.int32, "k_lens")
-    timed = _Stats.timed is not None and Lq == Lk
-    if timed:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+    cls = "attention" if Lq == Lk else "cross_attention"
+    ev = _t0(cls)
     rc = _lib.lib().m4d_attention_fwd(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Lq, Lk, N, D,
         q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
         _ptr(k_lens), float(softmax_scale) if softmax_scale else 0.0, int(accumulate), _stream())
     _lib.check(rc, "m4d_attention_fwd")
-    if timed:
-        ev1.record()
-        _Stats.timed["attention"].append((ev0, ev1, 4.0 * B * N * Lq * Lk * D))
+    _t1(cls, ev, 4.0 * B * N * Lq * Lk * D)
     return out
 
 
@@ -162,17 +178,12 @@ def attention_scatter(q: Tensor, k: Tensor, v: Tensor, outs, k_lens: Optional[Te
     ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
     if k_lens is not None:
         _req(k_lens, torch.int32, "k_lens")
-    timed = _Stats.timed is not None and Lq == Lk
-    if timed:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+    ev = _t0("attention")
     rc = _lib.lib().m4d_attention_fwd_scatter(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), ptrs, len(outs), R, B, Lq, Lk, N, D, q.stride(0), q.stride(1),
         k.stride(0), k.stride(1), outs[0].stride(0), outs[0].stride(1), _ptr(k_lens), 0.0, _stream())
     _lib.check(rc, "m4d_attention_fwd_scatter")
-    if timed:
-        ev1.record()
-        _Stats.timed["attention"].append((ev0, ev1, 4.0 * B * N * Lq * Lk * D))
+    _t1("attention", ev, 4.0 * B * N * Lq * Lk * D)
 
 
 def layernorm_modulate(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
@@ -200,12 +211,14 @@ def layernorm_modulate(x: Tensor, weight: Optional[Tensor] = None, bias: Optiona
                              f"(one slab per batch element), got {tuple(guidance.shape)}")
         sg_rows = guidance.shape[1]
         sg_stride = guidance.stride(0)
+    ev = _t0("rows")
     rc = _lib.lib().m4d_layernorm_modulate(
         x.data_ptr(), int(x.dtype == BF16), _ptr(weight), _ptr(bias), _ptr(shift), _ptr(scale),
         mod_batch_stride, rows, rows_per_batch or rows, C, eps, out.data_ptr(),
         int(out_dtype == torch.float32), _ptr(guidance), sg_stride, sg_rows, _ptr(guidance_gate),
         _stream())
     _lib.check(rc, "m4d_layernorm_modulate")
+    _t1("rows", ev, float(x.numel() * x.element_size() + out.numel() * out.element_size()))
     return out
 
 
@@ -221,10 +234,12 @@ def rmsnorm_rope_(x: Tensor, weight: Optional[Tensor], heads: int, eps: float = 
     if rope_cos is not None:
         _req(rope_cos, torch.float32, "rope_cos")
         _req(grid_fhw, torch.int32, "grid_fhw")
+    ev = _t0("rows")
     rc = _lib.lib().m4d_rmsnorm_rope(x.data_ptr(), x.stride(1), _ptr(weight), _ptr(rope_cos),
                                      _ptr(rope_sin), _ptr(grid_fhw), B, L, heads, C // heads, eps,
                                      _stream())
     _lib.check(rc, "m4d_rmsnorm_rope")
+    _t1("rows", ev, 4.0 * B * L * C)
     return x
 
 
@@ -530,23 +545,31 @@ def groupnorm_swish_cl(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-
     return out
 
 
-def softmax_rows(s: Tensor, scale: float) -> Tensor:
+def softmax_rows(s: Tensor, scale: float, out: Optional[Tensor] = None) -> Tensor:
+    """p = softmax(s * scale) row-wise; `out` may be a wider (zero-initialised) bf16 buffer view."""
     _lib.require_device()
     _req(s, torch.float32, "s")
     R, N = s.shape
-    p = torch.empty(R, N, device=s.device, dtype=BF16)
+    p = torch.empty(R, N, device=s.device, dtype=BF16) if out is None else out
+    _req(p, BF16, "out")
+    if p.shape != (R, N) or p.stride(1) != 1 or s.stride(1) != 1:
+        raise ValueError("more4d_b200.softmax_rows: shape / stride mismatch")
     rc = _lib.lib().m4d_softmax_rows(s.data_ptr(), p.data_ptr(), R, N, s.stride(0), p.stride(0), scale,
                                      _stream())
     _lib.check(rc, "m4d_softmax_rows")
     return p
 
 
-def transpose_bf16(x: Tensor) -> Tensor:
-    """[R, C] (row stride free) -> contiguous [C, R]."""
+def transpose_bf16(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """[R, C] (row stride free) -> [C, R] (contiguous, or the given view with a free row stride)."""
     _lib.require_device()
     _req(x, BF16, "x")
     R, C = x.shape
-    out = torch.empty(C, R, device=x.device, dtype=BF16)
-    rc = _lib.lib().m4d_transpose_bf16(x.data_ptr(), out.data_ptr(), R, C, x.stride(0), R, _stream())
+    if out is None:
+        out = torch.empty(C, R, device=x.device, dtype=BF16)
+    _req(out, BF16, "out")
+    if out.shape != (C, R) or out.stride(1) != 1:
+        raise ValueError("more4d_b200.transpose_bf16: `out` must be a [C, R] view with unit column stride")
+    rc = _lib.lib().m4d_transpose_bf16(x.data_ptr(), out.data_ptr(), R, C, x.stride(0), out.stride(0), _stream())
     _lib.check(rc, "m4d_transpose_bf16")
     return out

@@ -213,11 +213,17 @@ class AutoencoderKLWan(nn.Module):
         wq = self._p(name + ".to_qkv.weight").view(3 * C, C)
         qkv = ops.linear(y.view(T * L, C), wq, self._p(name + ".to_qkv.bias"))          # [T*L, 3C]
         o = torch.empty(T * L, C, device=x.device, dtype=BF16)
+        # the key dimension is the K of the second GEMM: padded to a multiple of 8 tokens (16-byte
+        # rows for TMA) with zero probabilities / zero V columns when H/8 * W/8 is not one
+        Lp = (L + 7) // 8 * 8
+        s = torch.empty(L, Lp, device=x.device, dtype=torch.float32)
+        p = torch.zeros(L, Lp, device=x.device, dtype=BF16) if Lp != L else torch.empty(L, L, device=x.device, dtype=BF16)
+        vt = torch.zeros(C, Lp, device=x.device, dtype=BF16) if Lp != L else torch.empty(C, L, device=x.device, dtype=BF16)
         for f in range(T):
             blk = qkv[f * L:(f + 1) * L]
-            s = ops.linear(blk[:, :C], blk[:, C:2 * C], None, ops.EPI_F32_RAW)          # [L, L] fp32
-            p = ops.softmax_rows(s, 1.0 / math.sqrt(C))
-            vt = ops.transpose_bf16(blk[:, 2 * C:])                                       # [C, L]
+            ops.linear(blk[:, :C], blk[:, C:2 * C], None, ops.EPI_F32_RAW, out=s[:, :L])   # [L, L] fp32 logits
+            ops.softmax_rows(s[:, :L], 1.0 / math.sqrt(C), out=p[:, :L])
+            ops.transpose_bf16(blk[:, 2 * C:], out=vt[:, :L])                               # [C, L]
             ops.linear(p, vt, None, out=o[f * L:(f + 1) * L])
         wp = self._p(name + ".proj.weight").view(C, C)
         out = ops.linear(o, wp, self._p(name + ".proj.bias"), ops.EPI_ADD_BF16, residual=x.view(T * L, C))

@@ -16,6 +16,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box via gpurun)")
 
 
+def pytest_sessionstart(session):
+    """Development builds only (-DM4D_DEV): M4D_DEV_FLAGS=0x122 runs the suite against a kernel variant."""
+    flags = os.environ.get("M4D_DEV_FLAGS")
+    if flags:
+        from more4d_b200 import _lib
+        _lib.dev_set_flags(int(flags, 0))
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

@@ -262,8 +262,44 @@ def vae_cases(vae_mod, traj_mod):
     print("vae", tuple(params.shape), tuple(rec.shape), float(rec.abs().mean()))
 
 
+def vae_bf16_case(vae_mod, traj_mod):
+    """The REAL reference VAE and adaptors run IN BF16 (weights, activations) on CPU — the dtype the
+    reference's inference path uses (pipeline_wan_fun_control.py:356-386 calls the VAE outside
+    autocast with weight_dtype bf16).  Every op of the path accepts bf16 on CPU (probed: Conv3d,
+    F.normalize, SiLU, nearest-exact Upsample via its own .float() round trip vae:67, SDPA,
+    GroupNorm).  Same inputs as vae_cases(); replaces the bf16-EMULATION argument for the
+    end-to-end tolerances (VERDICT r1 weak #1)."""
+    import contextlib, io
+    seed = 11
+    sd = synth.vae_state_dict(seed=seed)
+    m = vae_mod.AutoencoderKLWan().to(torch.bfloat16)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = synth._randn(seed, "vae.x", (1, 3, 13, 32, 48), 0.5, "cpu", torch.bfloat16)
+    z = synth._randn(seed, "vae.z", (1, 16, 4, 4, 6), 1.0, "cpu", torch.bfloat16)
+    out = {"enc_params": m.encode(x)[0].parameters.float().contiguous(),
+           "dec": m.decode(z).sample.float().contiguous(), "x_sum": checksum(x), "z_sum": checksum(z)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ea, da = traj_mod.VAEEncoderadaptor().to(torch.bfloat16), traj_mod.VAEDecoderadaptor().to(torch.bfloat16)
+    ea.load_state_dict(synth.adaptor_state_dict("encoder", seed), strict=True)
+    da.load_state_dict(synth.adaptor_state_dict("decoder", seed), strict=True)
+    tv = synth.trajectory_video(5, 32, 48, seed)
+    out["adaptor_enc"] = ea(tv).float().contiguous()
+    out["adaptor_dec"] = da(tv).float().contiguous()
+    # the whole Motion-Sensitive round trip (infer_vae.py:276-281 with .mode())
+    pseudo = ea(tv) * 2 - 1
+    lat = m.encode(pseudo)[0].mode()
+    rec = m.decode(lat).sample
+    out["rt_latent"], out["rt_video"], out["rt_out"] = (t.float().contiguous() for t in (lat, rec, da(rec)))
+    save_file(out, os.path.join(OUT, "vae_bf16.safetensors"))
+    print("vae_bf16", tuple(out["enc_params"].shape), tuple(out["rt_out"].shape))
+
+
 def main():
     t4d, _vae, _traj = ref_import.load()
+    if "--only-vae-bf16" in sys.argv:
+        vae_bf16_case(_vae, _traj)
+        return
     if "--only-14b" in sys.argv:
         block14b_case(t4d)
         return

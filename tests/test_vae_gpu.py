@@ -276,3 +276,111 @@ def test_adaptors_and_roundtrip(golden):
              out=rel_err(out.float().cpu(), ro))
     print({k: f"{v:.3e}" for k, v in e.items()})
     assert e["latent"] < 3e-2 and e["video"] < 5e-2 and e["out"] < 8e-2
+
+
+# --------------------------------------------------------------------------------------------
+# per-layer, teacher-forced parity (VERDICT r1 next #1c): every layer of the encoder and decoder
+# programs receives the ORACLE's input of that layer and must reproduce the oracle's output of that
+# layer to kernel-level accuracy — compounding over depth is taken out of the picture.
+# --------------------------------------------------------------------------------------------
+LAYER_TOL = 3e-3
+
+
+def _oracle_layer(kind, x, sd, p):
+    if kind == "conv":
+        return V.causal_conv3d(x, sd[p + ".weight"], sd[p + ".bias"], AR)
+    if kind == "res":
+        return V.residual_block(x, sd, p, AR)
+    if kind == "attn":
+        return V.attention_block(x, sd, p, AR)
+    if kind in ("down2d", "down3d"):
+        return V.downsample(x, sd, p, kind, AR)
+    if kind in ("up2d", "up3d"):
+        return V.upsample(x, sd, p, kind, AR)
+    if kind == "head":
+        y = V.silu(V.rms_norm(x, sd[p + ".0.gamma"], AR), AR)
+        return V.causal_conv3d(y, sd[p + ".2.weight"], sd[p + ".2.bias"], AR)
+    raise ValueError(kind)
+
+
+def _our_layer(m, kind, name, cin, cout, xg, next_gamma):
+    """One layer of the host mirror on a channels-last GPU tensor; returns (out, normed or None)."""
+    from more4d_b200 import ops
+    if kind == "conv":
+        return m._conv(xg, name, (3, 3, 3), cout, (2, 1, 1)), None
+    if kind == "res":
+        return m._res(xg, name, cin, cout, None, next_gamma)
+    if kind == "attn":
+        return m._attn(xg, name), None
+    if kind in ("down2d", "down3d"):
+        return m._down(xg, name, kind, cin), None
+    if kind in ("up2d", "up3d"):
+        return m._up(xg, name, kind, cin, next_gamma)
+    if kind == "head":
+        xn = ops.rmsnorm_silu_cl(xg, m._p(name + ".0.gamma"))
+        cpad = max(cout, 16)
+        return m._conv(xn, name + ".2", (3, 3, 3), cout, (2, 1, 1))[..., :cout] if cpad == cout else \
+            m._conv(xn, name + ".2", (3, 3, 3), cout, (2, 1, 1)), None
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("side", ["encoder", "decoder"])
+def test_vae_layerwise_teacher_forced(side):
+    from more4d_b200.vae_arch import WAN_VAE, decoder_layers, encoder_layers
+    sd = synth.vae_state_dict(seed=SEED)
+    m = _vae()
+    if side == "encoder":
+        layers = encoder_layers(WAN_VAE)
+        x = AR.r(synth._randn(SEED, "vae.x", (1, 3, 9, 32, 48), 0.5, "cpu", BF16).float())
+        # first layer consumes the 3-channel video: run it through the mirror's own input path
+        x = V.causal_conv3d(x, sd["model.encoder.conv1.weight"], sd["model.encoder.conv1.bias"], AR)
+        layers = layers[1:]
+    else:
+        layers = decoder_layers(WAN_VAE)
+        x = AR.r(synth._randn(SEED, "vae.z2", (1, 16, 3, 4, 6), 1.0, "cpu", BF16).float())
+        x = torch.cat([x, torch.zeros(1, 16, 3, 4, 6)], dim=1)        # the mirror keeps the latent in 32 channels
+    worst = {}
+    with torch.no_grad():
+        for i, (kind, name, cin, cout) in enumerate(layers):
+            p = "model." + name
+            xin = x[:, :cin] if kind == "conv" and x.shape[1] != cin else x
+            y = _oracle_layer(kind, xin, sd, p)
+            ng = m._next_gamma(layers, i, None)
+            if kind == "head" and cout < 16:
+                # 3-channel video head: the mirror writes planar output with the clamp fused (vae:827)
+                from more4d_b200 import ops
+                xn = ops.rmsnorm_silu_cl(_cl(x.to(BF16)), m._p(name + ".0.gamma"))
+                vid = torch.empty(cout, *xn.shape[:3], device="cuda", dtype=BF16)
+                m._conv(xn, name + ".2", (3, 3, 3), cout, (2, 1, 1), planar_out=vid, act=1)
+                got, want = vid.float().cpu().unsqueeze(0), y.clamp(-1, 1)
+                gn = None
+            else:
+                out, gn = _our_layer(m, kind, name, cin, cout, _cl(x.to(BF16)), ng)
+                got, want = _ncthw(out)[:, :y.shape[1]], y
+            e = rel_err(got, want)
+            worst[kind] = max(worst.get(kind, 0.0), e)
+            assert e < LAYER_TOL, (side, i, kind, name, e)
+            if gn is not None:          # fused epilogue: the consumer's SiLU(RMS_norm(.)) of the same output
+                nxt = "model." + layers[i + 1][1]
+                wn = V.silu(V.rms_norm(y, sd[nxt + ".residual.0.gamma"], AR), AR)
+                en = rel_err(_ncthw(gn), wn)
+                worst[kind + "+norm"] = max(worst.get(kind + "+norm", 0.0), en)
+                assert en < 5e-3, (side, i, kind, name, "fused norm", en)
+            x = y                                                    # teacher forcing
+    print(side, {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+def test_vae_attention_block_isolated():
+    """AttentionBlock (vae:227-266): RMS_norm -> to_qkv 1x1 -> per-frame
+    single-head attention with head_dim = C = 384 (GEMM -> row softmax -> GEMM on the validated GEMM
+    kernel) -> proj 1x1 (zero-initialised in the reference, non-zero here, F6) + residual."""
+    sd = synth.vae_state_dict(seed=SEED)
+    m = _vae()
+    for (T, H, W) in [(1, 4, 6), (3, 9, 13), (2, 16, 24)]:       # 24 / 117 / 384 tokens per frame
+        x = AR.r(_rand((1, 384, T, H, W), 50 + T, 1.5).float())
+        for name in ("encoder.middle.1", "decoder.middle.1"):
+            want = V.attention_block(x, sd, "model." + name, AR)
+            with torch.no_grad():
+                got = _ncthw(m._attn(_cl(x.to(BF16)), name))
+            assert rel_err(got, want) < 3e-3, (name, T, H, W)
+            assert rel_err(got - x, want - x) < 8e-3                # the attention branch itself, without the pass-through
