@@ -117,6 +117,67 @@ def cpu_reference_arm(args, cfg, L, grid, rank, repeats=1, skip=0):
     return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}, times
 
 
+def sequence_parallel_legs(args, cfg, model, den, dev, rank, world, frames, height, width, dp_ms_per_step):
+    """N > 1 only.  (1) bit-exactness of the Ulysses forward — both exchange forms, NCCL all-to-all and
+    the fused peer-memory stores — against the unsharded forward on a small model whose head count
+    divides N; (2) ONE sample of the headline workload sequence-sharded over the N GPUs (strong
+    scaling, single-sample latency): ms per latent-step, device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from more4d_b200 import config as mcfg, synth
+    from more4d_b200.dit import WanTransformer4DModel
+    from more4d_b200.pipeline import synthetic_conditioning
+    rec = {}
+    tiny = mcfg.WAN_TINY.with_(num_heads=8, dim=1024, ffn_dim=2048)
+    m = WanTransformer4DModel.from_config(tiny, device=dev)
+    m.load_state_dict(synth.dit_state_dict(tiny, 21), strict=True)
+    inp = synth.dit_inputs(tiny, (3, 5, 8), 2, 21)
+    kw = dict(x=inp["x"].to(dev), t=inp["t"].to(dev), context=[c.to(dev) for c in inp["context"]],
+              seq_len=inp["seq_len"], clip_fea=inp["clip_fea"].to(dev), y=inp["y"].to(dev),
+              full_ref=inp["full_ref"].to(dev))
+    ref = m(**kw)
+    flags = []
+    for mode, peer in (("nccl", False), ("peer", True)):
+        m.enable_multi_gpus_inference()
+        m.sp.peer_memory = peer
+        y1, y2 = m(**kw), m(**kw)                          # second call re-uses the exchange buffers
+        m.disable_multi_gpus_inference()
+        ok = torch.tensor([int(torch.equal(ref, y1) and torch.equal(ref, y2))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        rec[f"bit_exact_{mode}"] = bool(ok.item())
+        flags.append(bool(ok.item()))
+    rec["bit_exact"] = all(flags)
+    rec["bit_exact_model"] = "tiny DiT (C 1024, 8 heads, 2 layers, grid 3x5x8, CFG batch 2), both exchange forms, on every rank"
+    del m
+    # (2) headline workload, one sample over all ranks
+    lat_t = (frames - 1) // 4 + 1
+    lat_host, cond_host = synthetic_conditioning((1, 16, lat_t, height // 8, width // 8), seed=0, device="cpu",
+                                                 text_dim=cfg.text_dim, clip_dim=cfg.clip_dim)
+    lat, cond = lat_host.to(dev), cond_host.to(dev)
+    model.enable_multi_gpus_inference()
+    for s in range(2):
+        den.step(lat, s, cond)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.sp_steps):
+        den.step(lat, (2 + s) % den.num_inference_steps, cond)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.sp_steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    model.disable_multi_gpus_inference()
+    rec.update(ms_per_step=float(ms.item()), steps=args.sp_steps, scaling="strong",
+               latent_steps_per_s=1000.0 / float(ms.item()),
+               speedup_vs_one_gpu_step=dp_ms_per_step / float(ms.item()),
+               exchange="fused peer-memory stores (symmetric memory) + barrier; 2 exchanges per block",
+               note="one sample sequence-sharded over all ranks; `speedup` is against this run's per-GPU "
+                    "sample-sharded step time (= the 1-GPU step time under weak scaling)")
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -130,6 +191,9 @@ def main():
     ap.add_argument("--parallelism", default="sample", choices=["sample", "sp"],
                     help="sample: one sample per GPU (weak scaling, the default / headline); sp: ONE sample, "
                          "sequence sharded over the GPUs (Ulysses all-to-alls; strong scaling, single-sample latency)")
+    ap.add_argument("--no-vae", action="store_true", help="skip the Motion-Sensitive VAE round-trip sub-record (N=1)")
+    ap.add_argument("--no-sp", action="store_true", help="skip the sequence-parallel legs (N>1)")
+    ap.add_argument("--sp-steps", type=int, default=10)
     ap.add_argument("--hoist-conditioning", action="store_true",
                     help="compute the step-invariant context embedding / cross-attention K/V once instead of "
                          "per step (bit-identical; NOT the default: the reference recomputes them every step)")
@@ -264,6 +328,34 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = units * args.steps / float(e2e_s.item())
 
+    # ---- per-kernel-class device time: ONE extra step outside the timed region with every launch of the
+    # block kernels bracketed by events (name what grows with N); reported for the slowest rank
+    ops.start_kernel_timing(("attention", "cross_attention", "gemm", "rows"))
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    run(1, lat, args.warmup + args.steps)
+    pe1.record()
+    torch.cuda.synchronize()
+    prof = ops.stop_kernel_timing()
+    cls_ms = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in prof.items()}
+    cls_ms["step"] = pe0.elapsed_time(pe1)
+    cls_ms["other"] = cls_ms["step"] - sum(v for k, v in cls_ms.items() if k != "step")
+    keys = sorted(cls_ms)
+    cm = torch.tensor([cls_ms[k] for k in keys], device=dev)
+    if world > 1:
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+    kernel_class_ms = {k: float(v) for k, v in zip(keys, cm.tolist())}
+    kernel_class_ms["gemm_tflops"] = sum(w for _, _, w in prof["gemm"]) / (cls_ms["gemm"] / 1e3) / 1e12 if cls_ms["gemm"] else None
+    kernel_class_ms["note"] = ("one step with per-launch CUDA events on every block kernel (max over ranks per class); "
+                               "`other` = embeddings, head, CFG/Euler, host gaps")
+
+    # ---- N > 1: the sequence-parallel path under the driver (VERDICT r1 #1d, #5)
+    sp_record = None
+    if world > 1 and not args.no_sp and cfg.num_heads % world == 0 and not visim:
+        sp_record = sequence_parallel_legs(args, cfg, model, den, dev, rank, world, frames, height, width,
+                                           ms_total / args.steps)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -275,21 +367,37 @@ def main():
     att_fl = att[0][2] if att else 0.0
     avg_ms = sum(att_ms) / max(1, len(att_ms))
     achieved = att_fl / (avg_ms / 1e3) / 1e12 if att else 0.0
-    traffic = None
+    # DRAM bytes per launch of the SHIPPED kernel at this workload's shape, from its committed ncu
+    # summary (profiles/attention_traffic.json names the capture it was read from)
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "attention_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload)
+            tj = json.load(f)
+        traffic, traffic_source = tj.get(args.workload), tj.get("source")
     roofline = {"kernel": "attn_fwd_d128_kernel (self-attention launches, Lq=Lk=L)", "bound": "tensor",
                 "achieved": achieved, "peak": sust, "unit": "TFLOP/s", "frac": achieved / sust,
                 "frac_of_burst_peak": achieved / burst, "peak_source": f"{src} bf16 sustained (kernel timed inside a long step)",
                 "launches_timed": len(att), "avg_launch_ms": avg_ms,
                 "share_of_step": sum(att_ms) / ms_total if ms_total else None,
-                "algorithmic_flops_per_launch": att_fl, "traffic": traffic}
+                "algorithmic_flops_per_launch": att_fl, "traffic": traffic, "traffic_source": traffic_source}
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference_arm(args, cfg, L, grid, rank)
+
+    # ---- BASELINE.json configs[3]: Motion-Sensitive VAE encode+decode at 49x720x1280 (N=1 only)
+    vae_record = None
+    if world == 1 and not args.no_vae and args.workload.startswith("720p"):
+        del model, den
+        torch.cuda.empty_cache()
+        from tools import bench_vae
+        vae_record = bench_vae.run(frames, height, width, iters=2, dev=dev)
+        vae_record["frac_of_sustained_tensor_peak"] = vae_record["conv_tflops_total"] / sust
+        vae_record["roofline_note"] = ("conv FLOPs 6.92e14 (BASELINE.md §3) / total_ms against the measured sustained "
+                                       "bf16 peak; the convolutions are tensor-bound, norms / resampling HBM-bound")
+        if not args.no_cpu_baseline:
+            vae_record["cpu_baseline"] = bench_vae.cpu_sample(threads=len(os.sched_getaffinity(0)))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -297,7 +405,9 @@ def main():
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "dit_forwards_per_s": value * 2,
-            "roofline": roofline, "cpu_baseline": cb}
+            "roofline": roofline, "cpu_baseline": cb, "kernel_class_ms": kernel_class_ms,
+            "vae_roundtrip": vae_record, "sp": sp_record,
+            "sp_bit_exact": None if sp_record is None else sp_record.get("bit_exact")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -203,6 +203,97 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
   }
 }
 
+// Same arithmetic, ONE WARP PER ROW with 16-byte vectors — the shape the DiT runs (head_dim 128,
+// C <= 5120).  The CTA-per-row kernel above moves 8 bytes per load, five loads per thread, and
+// pays two block reductions per row: 2.6 TB/s = 0.40 of the measured HBM copy peak at
+// [2, 50400, 5120] (profiles/rows_r02.md).  Here a lane owns the 16-byte vectors lane, lane + 32,
+// ... of its row (up to 20 loads of 16 B in flight per lane), the sum of squares is reduced with
+// shuffles only, and — because 32 vectors span exactly two 128-channel heads — every vector of a
+// lane covers the SAME four rotary pairs (lane % 16) * 4 .. + 3 of some head: the lane fetches its
+// four (cos, sin) pairs once per row instead of two table loads per pair and head.
+constexpr int RW_MAXV = 20;          // 16-byte vectors per lane: C <= 32 * 8 * 20 = 5120
+constexpr int RW_WARPS = 8;
+__global__ void __launch_bounds__(RW_WARPS * 32)
+rmsnorm_rope_warp_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
+                         const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
+                         const int* __restrict__ grid_fhw, long long rows, int L, int C, float eps,
+                         long long row_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * RW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = static_cast<int>(row / L);
+  const int l = static_cast<int>(row - static_cast<long long>(b) * L);
+  bf16* xr = x + row * row_stride;
+  const int nvec = C >> 3;
+  uint4 v[RW_MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < RW_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      v[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
+        ss += lo * lo + hi * hi;
+      }
+    }
+  }
+  float rstd = 1.f;
+  if (weight != nullptr) rstd = bf16_round(rsqrtf(warp_sum(ss) / C + eps));
+
+  bool rope = false;
+  float cs[4], sn[4];
+  if (rope_cos != nullptr) {
+    const int F = grid_fhw[b * 3 + 0], H = grid_fhw[b * 3 + 1], W = grid_fhw[b * 3 + 2];
+    if (l < F * H * W) {
+      rope = true;
+      const int pf = l / (H * W);
+      const int rem = l - pf * H * W;
+      const int ph = rem / W;
+      const int pw = rem - ph * W;
+      const int pair0 = (lane & 15) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int pi = pair0 + k;                  // 22 frame | 21 row | 21 col pairs (t4d:346,928-935)
+        const int pos = pi < 22 ? pf : (pi < 43 ? ph : pw);
+        cs[k] = __ldg(rope_cos + pos * 64 + pi);
+        sn[k] = __ldg(rope_sin + pos * 64 + pi);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RW_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t g[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
+      if (weight != nullptr) {
+        const uint4 gw = __ldg(reinterpret_cast<const uint4*>(weight + vi * 8));
+        g[0] = gw.x; g[1] = gw.y; g[2] = gw.z; g[3] = gw.w;
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float re = __uint_as_float(w[e] << 16), im = __uint_as_float(w[e] & 0xFFFF0000u);
+        if (weight != nullptr) {
+          re = bf16_round(bf16_round(re * rstd) * __uint_as_float(g[e] << 16));
+          im = bf16_round(bf16_round(im * rstd) * __uint_as_float(g[e] & 0xFFFF0000u));
+        }
+        if (rope) {
+          const float r2 = re * cs[e] - im * sn[e];
+          const float i2 = re * sn[e] + im * cs[e];
+          re = r2;
+          im = i2;
+        }
+        o[e] = pack_bf16(re, im);
+      }
+      *reinterpret_cast<uint4*>(xr + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // y[M,N] (fp32) = act(x[M,K] fp32) . W[N,K]^T (bf16) + b   for M <= 8 rows: the time-embedding
 // MLPs, which the reference runs under autocast(float32) (t4d:1160-1171).  HBM-bound on W:
@@ -504,6 +595,15 @@ extern "C" int m4d_rmsnorm_rope(void* x, long long row_stride, const void* weigh
               M4D_ERR_ALIGN);
   const long long rows = static_cast<long long>(B) * L;
   M4D_REQUIRE(rows < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  if (head_dim == 128 && C <= 32 * 8 * RW_MAXV && row_stride % 8 == 0 && aligned16(x) &&
+      (weight == nullptr || aligned16(weight))) {
+    const unsigned grid = static_cast<unsigned>((rows + RW_WARPS - 1) / RW_WARPS);
+    rmsnorm_rope_warp_kernel<<<grid, RW_WARPS * 32, 0, stream>>>(
+        static_cast<bf16*>(x), static_cast<const bf16*>(weight), rope_cos, rope_sin, grid_fhw, rows, L, C, eps,
+        row_stride);
+    M4D_CHECK_LAUNCH("rmsnorm_rope_warp_kernel");
+    return M4D_OK;
+  }
   rmsnorm_rope_kernel<<<static_cast<unsigned>(rows), ROW_THREADS, 0, stream>>>(
       static_cast<bf16*>(x), static_cast<const bf16*>(weight), rope_cos, rope_sin, grid_fhw, L, C,
       head_dim, eps, row_stride);

@@ -170,6 +170,38 @@ def mpm_model_case(name="dit_tiny_mpm", seed=8):
     print(name, tuple(y.shape), float(y.abs().mean()), tuple(captured["adapter_out"].shape))
 
 
+TEACACHE_TS = [999.0, 990.0, 975.0, 940.0, 900.0, 700.0, 650.0, 400.0]
+TEACACHE_KW = dict(coefficients=[0.0, 0.0, 0.0, 1.0, 0.0], rel_l1_thresh=0.5, num_skip_start_steps=1)
+
+
+def teacache_case(t4d, name="dit_tiny_teacache", seed=4):
+    """The REAL model with the reference's own TeaCache (MoRe4D/models/cache_utils.py, hooks
+    t4d:1200-1270,1336-1339) over 8 steps of a toy Euler loop: the per-step skip decisions and outputs
+    (skipped steps re-use the previous residual of the block stack)."""
+    cfg, grid, batch = WAN_TINY, (3, 4, 6), 2
+    sd = synth.dit_state_dict(cfg, seed)
+    m = t4d.WanTransformer4DModel(
+        model_type="i2v", in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim, num_heads=cfg.num_heads,
+        num_layers=cfg.num_layers, text_dim=cfg.text_dim, text_len=cfg.text_len, add_ref_conv=True,
+        use_dino_guidance=False, use_omnimae_guidance=False)
+    m.load_state_dict(f32(sd), strict=True)
+    m.eval()
+    inp = synth.dit_inputs(cfg, grid, batch, seed)
+    m.enable_teacache(TEACACHE_KW["coefficients"], len(TEACACHE_TS), rel_l1_thresh=TEACACHE_KW["rel_l1_thresh"],
+                      num_skip_start_steps=TEACACHE_KW["num_skip_start_steps"], offload=False)
+    x = inp["x"].float()
+    ys, dec = [], []
+    for t in TEACACHE_TS:
+        y = m(x=x, t=torch.tensor([t, t]), context=[c.float() for c in inp["context"]], seq_len=inp["seq_len"],
+              clip_fea=inp["clip_fea"].float(), y=inp["y"].float(), full_ref=inp["full_ref"].float())
+        ys.append(y)
+        dec.append(int(bool(m.should_calc)))
+        x = (x - 0.05 * y).to(torch.bfloat16).float()              # toy Euler update, bf16 latents like the loop
+    save_file({"y": torch.stack(ys).contiguous(), "should_calc": torch.tensor(dec, dtype=torch.int32),
+               "x_sum": checksum(inp["x"])}, os.path.join(OUT, name + ".safetensors"))
+    print(name, dec)
+
+
 def model3d_case(t3d, name, cfg: DiTConfig, grid, batch, seed):
     """Real WanTransformer3DModel (the 4D-ViSM / Wan-InP backbone): in_dim 36, no reference conv."""
     sd = synth.dit_state_dict(cfg, seed)
@@ -302,6 +334,9 @@ def main():
         return
     if "--only-14b" in sys.argv:
         block14b_case(t4d)
+        return
+    if "--only-teacache" in sys.argv:
+        teacache_case(t4d)
         return
     if "--only-mpm" in sys.argv:
         mpm_model_case()

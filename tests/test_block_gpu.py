@@ -144,6 +144,40 @@ def test_teacache_skips_block_stack():
     model.disable_teacache()
 
 
+def test_teacache_numerics_match_the_reference(golden):
+    """TeaCache against the REAL model + the reference's own TeaCache (golden dit_tiny_teacache,
+    tests/golden/make_golden.py::teacache_case): the same skip pattern over an 8-step toy Euler loop
+    and the same outputs on computed AND on skipped steps (a skipped step adds the cached residual of
+    the block stack to the new embedding, t4d:1222-1227), teacher-forced on the reference's latents so
+    that bf16 drift of the loop does not enter."""
+    from more4d_b200.dit import WanTransformer4DModel
+    from tests.golden.make_golden import TEACACHE_KW, TEACACHE_TS
+    g = golden("dit_tiny_teacache")
+    cfg, grid, seed = WAN_TINY, (3, 4, 6), 4
+    sd = synth.dit_state_dict(cfg, seed)
+    inp = synth.dit_inputs(cfg, grid, 2, seed)
+    model = WanTransformer4DModel.from_config(cfg, device="cuda")
+    model.load_state_dict(sd, strict=True)
+    model.enable_teacache(TEACACHE_KW["coefficients"], len(TEACACHE_TS), rel_l1_thresh=TEACACHE_KW["rel_l1_thresh"],
+                          num_skip_start_steps=TEACACHE_KW["num_skip_start_steps"], offload=False)
+    kw = dict(context=[c.cuda() for c in inp["context"]], seq_len=inp["seq_len"], clip_fea=inp["clip_fea"].cuda(),
+              y=inp["y"].cuda(), full_ref=inp["full_ref"].cuda())
+    x = inp["x"].float()
+    want = [bool(v) for v in g["should_calc"].tolist()]
+    got, errs = [], []
+    with torch.no_grad():
+        for i, t in enumerate(TEACACHE_TS):
+            y = model(x=x.to(BF16).cuda(), t=torch.tensor([t, t]).cuda(), **kw)
+            got.append(bool(model.teacache.should_calc) if i + 1 < len(TEACACHE_TS) else want[-1])   # reset after the last step
+            errs.append(rel_err(y.float().cpu(), g["y"][i]))
+            x = (x - 0.05 * g["y"][i]).to(BF16).float()            # the reference's own trajectory
+    print("teacache:", got, [f"{e:.2e}" for e in errs])
+    assert got == want
+    assert max(errs) < 1e-2                                        # bf16 output tensor, as for dit_tiny
+    skipped = [e for e, w in zip(errs, want) if not w]
+    assert skipped and max(skipped) < 1e-2
+
+
 def test_hoisted_conditioning_is_bit_identical():
     """the context embedding and every block's cross-attention K/V do not
     depend on the timestep; computing them once (`precompute_conditioning`) must give exactly the

@@ -147,3 +147,33 @@ def test_model_with_motion_perception_front_end(golden):
                       clip_fea=inp["clip_fea"].float(), y=inp["y"].float(), full_ref=inp["full_ref"].float(),
                       guidance=feats)
     assert rel_err(y, g["y"]) < TOL
+
+
+def test_teacache_decisions_match_the_reference(golden):
+    """`cache_utils.teacache_decide / teacache_step_done` (the decision block the CUDA mirror runs,
+    dit._forward) on the oracle's e0 sequence reproduce the skip pattern of the REAL model with the
+    reference's own TeaCache (golden dit_tiny_teacache) — with our TeaCache class and with a
+    duck-typed object carrying only the reference's fields."""
+    import types
+    import numpy as np
+    from more4d_b200.cache_utils import TeaCache, teacache_decide, teacache_step_done
+    from tests.golden.make_golden import TEACACHE_KW, TEACACHE_TS
+    g = golden("dit_tiny_teacache")
+    sd = synth.dit_state_dict(WAN_TINY, 4)
+    want = [bool(v) for v in g["should_calc"].tolist()]
+    assert True in want and False in want                       # the case exercises both branches
+    ours = TeaCache(TEACACHE_KW["coefficients"], len(TEACACHE_TS), rel_l1_thresh=TEACACHE_KW["rel_l1_thresh"],
+                    num_skip_start_steps=TEACACHE_KW["num_skip_start_steps"], offload=False)
+    duck = types.SimpleNamespace(cnt=0, num_steps=len(TEACACHE_TS), num_skip_start_steps=TEACACHE_KW["num_skip_start_steps"],
+                                 rel_l1_thresh=TEACACHE_KW["rel_l1_thresh"], accumulated_rel_l1_distance=0,
+                                 rescale_func=np.poly1d(TEACACHE_KW["coefficients"]), previous_modulated_input=None,
+                                 should_calc=True, previous_residual=None, previous_residual_cond=None,
+                                 previous_residual_uncond=None)
+    for tc in (ours, duck):
+        got = []
+        for t in TEACACHE_TS:
+            _, e0 = O.time_embed(torch.tensor([t, t]), sd, WAN_TINY.freq_dim, WAN_TINY.dim)
+            got.append(teacache_decide(tc, e0, True))
+            teacache_step_done(tc, True)
+        assert got == want
+        assert tc.cnt == 0 and tc.previous_modulated_input is None      # reset after num_steps, t4d:1336-1339

@@ -88,7 +88,7 @@ def run(frames=49, height=720, width=1280, iters=2, dev="cuda", e2e=True):
     return line
 
 
-def cpu_sample(threads=None, latent_frames=2, height=720, width=1280):
+def cpu_sample(threads=None, latent_frames=1, height=720, width=1280):
     """CPU baseline of the VAE ("ONE VAE chunk at full resolution"): the oracle port
     (fp32) decoding `latent_frames` latent frames (= 1 + 4*(n-1) video frames) at full resolution on
     the host cores; extrapolated to the whole round trip by conv FLOPs (stated in the record)."""
