@@ -248,6 +248,29 @@ int m4d_project_points(const float* points, const float* colors, const float* wo
                        const float* intrinsic, long long N, int H, int W, unsigned char* image,
                        unsigned char* mask, void* workspace, long long workspace_bytes, void* stream);
 
+/* Forward 3D-Gaussian-splatting render of V views in one launch sequence — `gs_render` /
+ * `render_cuda` (MoRe4D/utils/gaussian_splatting.py:13-43,201-281) + the third-party
+ * GaussianRasterizer it calls once per frame (README.md:60; scripts/inference/infer.py:260-273,
+ * 398-444).  Published algorithm of that extension: projection + EWA covariance with 0.3 px
+ * dilation, 16x16 tiles, depth-sorted front-to-back alpha blending (1/255 and 1e-4 cut-offs).
+ * means: DEVICE fp32 [V, N, 3] (view stride in elements, 0 = shared); colors: DEVICE fp32 [N, 3] in
+ * 0..1 (view stride likewise; precomputed colours, use_sh=False); opacity: DEVICE fp32 [N]; cov3d:
+ * DEVICE fp32 [6] = xx xy xz yy yz zz of the ONE covariance all gaussians share
+ * (build_covariance(scale, rotation), :140-151); cams: DEVICE fp32 [V, 20], 16-byte aligned: rows of
+ * the world->camera [R|t] (12), fx fy in pixels, tan(fov_x/2) tan(fov_y/2), then P00 P11 P22 P23 of
+ * get_projection_matrix (:198-226).  image: DEVICE fp32 [V, 3, H, W]; image_u8 (or NULL): DEVICE
+ * uint8 [V, H, W, 3] = trunc(image * 255) (infer.py:272-273).  workspace: DEVICE, 16-byte aligned,
+ * >= m4d_gs_render_workspace(N, V, H, W, dup_capacity) bytes, dup_capacity = room for (tile,
+ * gaussian) pairs; *dup_needed (HOST, may be NULL) receives the count the call needs, and
+ * M4D_ERR_WORKSPACE is returned if it exceeds dup_capacity (nothing is rendered then).  The call
+ * synchronises the stream once (to read that count), like the original extension. */
+long long m4d_gs_render_workspace(long long N, int V, int H, int W, long long dup_capacity);
+int m4d_gs_render(const float* means, long long means_view_stride, const float* colors,
+                  long long colors_view_stride, const float* opacity, const float* cov3d, const float* cams,
+                  long long N, int V, int H, int W, float bg0, float bg1, float bg2, float* image,
+                  unsigned char* image_u8, void* workspace, long long workspace_bytes, long long dup_capacity,
+                  long long* dup_needed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

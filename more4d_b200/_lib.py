@@ -54,6 +54,8 @@ _SIGNATURES = {
     "m4d_transpose_bf16": (c_int, [_P, _P, _I, _I, _L, _L, _P]),
     "m4d_im2col3x3_cl": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "m4d_bilinear_repeat_cl": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "m4d_gs_render_workspace": (c_longlong, [_L, _I, _I, _I, _L]),
+    "m4d_gs_render": (c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _I, _F, _F, _F, _P, _P, _P, _L, _L, _P, _P]),
     "m4d_project_points_workspace": (c_longlong, [_L, _I, _I]),
     "m4d_project_points": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P]),
 }

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmore4d_sm100.so")
-SOURCES = ["gemm.cu", "gemm2.cu", "attention.cu", "elementwise.cu", "conv.cu", "conv_halo.cu", "vae_elementwise.cu", "project.cu", "mpm.cu"]
+SOURCES = ["gemm.cu", "gemm2.cu", "attention.cu", "elementwise.cu", "conv.cu", "conv_halo.cu", "vae_elementwise.cu", "project.cu", "mpm.cu", "gsplat.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
