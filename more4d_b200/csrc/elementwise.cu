@@ -60,15 +60,14 @@ layernorm_modulate_kernel(const TIn* __restrict__ x, const bf16* __restrict__ we
   const TIn* xr = x + row * C;
   const int nvec = C >> 2;
   float4 v[ROW_MAXV];
+#pragma unroll
+  for (int i = 0; i < ROW_MAXV; ++i) {          // every load of the row in flight before the first use
+    const int vi = threadIdx.x + i * ROW_THREADS;
+    v[i] = vi < nvec ? load4(xr + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < ROW_MAXV; ++i) {
-    const int vi = threadIdx.x + i * ROW_THREADS;
-    if (vi < nvec) {
-      v[i] = load4(xr + vi * 4);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
+  for (int i = 0; i < ROW_MAXV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = block_sum(s, red) / C;
   float ss = 0.f;
 #pragma unroll
@@ -203,45 +202,57 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
   }
 }
 
-// Same arithmetic, ONE WARP PER ROW with 16-byte vectors — the shape the DiT runs (head_dim 128,
+// Same arithmetic, TWO WARPS PER ROW with 16-byte vectors — the shape the DiT runs (head_dim 128,
 // C <= 5120).  The CTA-per-row kernel above moves 8 bytes per load, five loads per thread, and
 // pays two block reductions per row: 2.6 TB/s = 0.40 of the measured HBM copy peak at
-// [2, 50400, 5120] (profiles/rows_r02.md).  Here a lane owns the 16-byte vectors lane, lane + 32,
-// ... of its row (up to 20 loads of 16 B in flight per lane), the sum of squares is reduced with
-// shuffles only, and — because 32 vectors span exactly two 128-channel heads — every vector of a
+// [2, 50400, 5120] (profiles/rows_r02.md).  Here a lane owns every other 32-vector group of its row (up to 10 loads of 16 B in flight per
+// lane, ~90 registers, three CTAs per SM), the sum of squares is reduced with shuffles plus one
+// shared-memory exchange between the two warps, and — because 32 vectors span exactly two 128-channel heads — every vector of a
 // lane covers the SAME four rotary pairs (lane % 16) * 4 .. + 3 of some head: the lane fetches its
 // four (cos, sin) pairs once per row instead of two table loads per pair and head.
-constexpr int RW_MAXV = 20;          // 16-byte vectors per lane: C <= 32 * 8 * 20 = 5120
-constexpr int RW_WARPS = 8;
-__global__ void __launch_bounds__(RW_WARPS * 32)
+constexpr int RW_MAXV = 10;          // 16-byte vectors per lane: C <= 2 warps * 32 lanes * 8 * 10 = 5120
+constexpr int RW_WARPS = 8;          // per CTA: 4 rows x 2 warps
+__global__ void __launch_bounds__(RW_WARPS * 32, 2)
 rmsnorm_rope_warp_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
                          const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
                          const int* __restrict__ grid_fhw, long long rows, int L, int C, float eps,
                          long long row_stride) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * RW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float part[RW_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = warp & 1;                       // which half of the row's vectors this warp owns
+  long long row = static_cast<long long>(blockIdx.x) * (RW_WARPS / 2) + (warp >> 1);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;                     // keep the warp in step with the CTA barrier below
   const int b = static_cast<int>(row / L);
   const int l = static_cast<int>(row - static_cast<long long>(b) * L);
   bf16* xr = x + row * row_stride;
   const int nvec = C >> 3;
   uint4 v[RW_MAXV];
+  // all loads of the row are issued before the first use: with load and accumulate in one loop the
+  // compiler kept them in program order and a row cost ~20 dependent DRAM round trips (measured:
+  // 2.4 TB/s, profiles/rows_r02.md, first version of this kernel)
+#pragma unroll
+  for (int i = 0; i < RW_MAXV; ++i) {
+    const int vi = lane + (2 * i + wr) * 32;
+    v[i] = vi < nvec ? __ldcs(reinterpret_cast<const uint4*>(xr + vi * 8)) : make_uint4(0, 0, 0, 0);
+  }
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < RW_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      v[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
-        ss += lo * lo + hi * hi;
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
+      ss += lo * lo + hi * hi;
     }
   }
   float rstd = 1.f;
-  if (weight != nullptr) rstd = bf16_round(rsqrtf(warp_sum(ss) / C + eps));
+  if (weight != nullptr) {
+    ss = warp_sum(ss);
+    if (lane == 0) part[warp] = ss;
+    __syncthreads();
+    rstd = bf16_round(rsqrtf((part[warp & ~1] + part[warp | 1]) / C + eps));   // same order in both warps
+  }
 
   bool rope = false;
   float cs[4], sn[4];
@@ -263,16 +274,19 @@ rmsnorm_rope_warp_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
       }
     }
   }
+  // the norm weight (10 KB, L1/L2 resident) is fetched one vector ahead of its use
+  const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  const int v0 = lane + wr * 32;
+  uint4 gw_next = (weight != nullptr && v0 < nvec) ? __ldg(reinterpret_cast<const uint4*>(weight + v0 * 8)) : ones;
 #pragma unroll
   for (int i = 0; i < RW_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+    const int vi = lane + (2 * i + wr) * 32;
+    const uint4 gw = gw_next;
+    if (i + 1 < RW_MAXV && weight != nullptr && vi + 64 < nvec)
+      gw_next = __ldg(reinterpret_cast<const uint4*>(weight + (vi + 64) * 8));
+    if (live && vi < nvec) {
       const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      uint32_t g[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
-      if (weight != nullptr) {
-        const uint4 gw = __ldg(reinterpret_cast<const uint4*>(weight + vi * 8));
-        g[0] = gw.x; g[1] = gw.y; g[2] = gw.z; g[3] = gw.w;
-      }
+      const uint32_t g[4] = {gw.x, gw.y, gw.z, gw.w};
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -595,9 +609,9 @@ extern "C" int m4d_rmsnorm_rope(void* x, long long row_stride, const void* weigh
               M4D_ERR_ALIGN);
   const long long rows = static_cast<long long>(B) * L;
   M4D_REQUIRE(rows < (1ll << 31), M4D_ERR_BAD_SHAPE);
-  if (head_dim == 128 && C <= 32 * 8 * RW_MAXV && row_stride % 8 == 0 && aligned16(x) &&
+  if (head_dim == 128 && C <= 2 * 32 * 8 * RW_MAXV && row_stride % 8 == 0 && aligned16(x) &&
       (weight == nullptr || aligned16(weight))) {
-    const unsigned grid = static_cast<unsigned>((rows + RW_WARPS - 1) / RW_WARPS);
+    const unsigned grid = static_cast<unsigned>((rows + RW_WARPS / 2 - 1) / (RW_WARPS / 2));
     rmsnorm_rope_warp_kernel<<<grid, RW_WARPS * 32, 0, stream>>>(
         static_cast<bf16*>(x), static_cast<const bf16*>(weight), rope_cos, rope_sin, grid_fhw, rows, L, C, eps,
         row_stride);

@@ -70,8 +70,9 @@ def main():
     pl = rn(3, T, H, W)
     cases.append(("planar_to_cl [3,4,720,1280] -> [...,16]", pl.numel() * 2 + T * H * W * 16 * 2,
                   lambda: ops.planar_to_cl(pl, 16)))
-    cases.append(("cl_to_planar [4,720,1280,96] -> [96,...]", a96.numel() * 4,
-                  lambda: ops.cl_to_planar(a96)))
+    enc_out = rn(13, 90, 160, 32)                     # where the VAE uses it: the encoder's 32-channel output
+    cases.append(("cl_to_planar [13,90,160,32] -> [32,...] (encoder output)", enc_out.numel() * 4,
+                  lambda: ops.cl_to_planar(enc_out)))
     s = rn(14400, 14400, dt=torch.float32)
     cases.append(("softmax_rows fp32 [14400,14400] -> bf16 (VAE attention)", s.numel() * 6,
                   lambda: ops.softmax_rows(s, 384 ** -0.5)))
