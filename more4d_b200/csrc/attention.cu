@@ -577,7 +577,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld32(tS + 64, s + 64);
         tmem_ld32(tS + 96, s + 96);
         reg_fence32(s + 0);
-        if (valid < 32) {
+        if (__builtin_expect(valid < 32, 0)) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (i >= valid) s[i] = 0xFF800000u;    // -inf
@@ -588,13 +588,13 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         reg_fence32(s + 32);
         reg_fence32(s + 64);
         reg_fence32(s + 96);
-        if (valid < A_BKV) {
+        if (__builtin_expect(valid < A_BKV, 0)) {
 #pragma unroll
           for (int i = 32; i < 128; ++i)
             if (i >= valid) s[i] = 0xFF800000u;
         }
         exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
-        if (__any_sync(0xffffffffu, (j == 0) || !(l0 + l1 < A_SUM_GUARD))) {
+        if (__builtin_expect(__any_sync(0xffffffffu, (j == 0) || !(l0 + l1 < A_SUM_GUARD)), 0)) {
           // exact path for the whole tile: S is intact (nothing of this tile has been stored);
           // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled
           const bool mine = (j == 0) || !(l0 + l1 < A_SUM_GUARD);
@@ -636,7 +636,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // ---- second half
         float h0 = 0.f, h1 = 0.f;
         exp_pipe<PP, 32, 32>(s, ph, c, neg_mc, h0, h1);
-        if (__any_sync(0xffffffffu, !(h0 + h1 < A_SUM_GUARD))) {
+        if (__builtin_expect(__any_sync(0xffffffffu, !(h0 + h1 < A_SUM_GUARD)), 0)) {
           // the first half is with the tensor pipe at the old reference: wait for its MMAs,
           // then move the reference (true max of the second half), rescale O / l, redo the half
           const bool mine = !(h0 + h1 < A_SUM_GUARD);

@@ -122,6 +122,84 @@ layernorm_modulate_kernel(const TIn* __restrict__ x, const bf16* __restrict__ we
   }
 }
 
+// The DiT's hot instance — fp32 residual stream in, bf16 out, C <= 5120, no Motion-Perception
+// injection — with FOUR WARPS PER ROW, two rows per CTA: a lane keeps 10 float4 of its row in
+// registers, the two statistics are reduced with shuffles + one shared-memory exchange under a
+// 128-thread named barrier each (the CTA-per-row kernel above pays four __syncthreads of 256
+// threads per row and a CTA launch per 20 KB: 4.5 TB/s = 0.70 of the HBM copy peak,
+// profiles/rows_r02.md).  Same arithmetic, same summation tree per lane.
+constexpr int LW_MAXV = 10;
+__global__ void __launch_bounds__(256, 3)
+layernorm_modulate_wg_kernel(const float* __restrict__ x, const bf16* __restrict__ weight,
+                             const bf16* __restrict__ bias, const float* __restrict__ shift,
+                             const float* __restrict__ scale, long long mod_bstride, long long rows,
+                             int rows_per_batch, int C, float eps, bf16* __restrict__ out) {
+  __shared__ float red[2][2][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = warp >> 2, wq = warp & 3;
+  long long row = static_cast<long long>(blockIdx.x) * 2 + slot;
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
+  const float* xr = x + row * C;
+  const int nvec = C >> 2;
+  float4 v[LW_MAXV];
+#pragma unroll
+  for (int i = 0; i < LW_MAXV; ++i) {
+    const int vi = lane + (4 * i + wq) * 32;
+    v[i] = vi < nvec ? __ldcs(reinterpret_cast<const float4*>(xr + vi * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LW_MAXV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  s = warp_sum(s);
+  if (lane == 0) red[slot][0][wq] = s;
+  named_bar_sync(1 + slot, 128);
+  const float mean = ((red[slot][0][0] + red[slot][0][1]) + (red[slot][0][2] + red[slot][0][3])) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LW_MAXV; ++i) {
+    const int vi = lane + (4 * i + wq) * 32;
+    if (vi < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[slot][1][wq] = ss;
+  named_bar_sync(1 + slot, 128);
+  const float rstd = rsqrtf(((red[slot][1][0] + red[slot][1][1]) + (red[slot][1][2] + red[slot][1][3])) / C + eps);
+  const long long batch = row / rows_per_batch;
+  const float* sh = shift ? shift + batch * mod_bstride : nullptr;
+  const float* sc = scale ? scale + batch * mod_bstride : nullptr;
+  bf16* orow = out + row * C;
+#pragma unroll
+  for (int i = 0; i < LW_MAXV; ++i) {
+    const int vi = lane + (4 * i + wq) * 32;
+    if (live && vi < nvec) {
+      const int c0 = vi * 4;
+      float4 y = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd,
+                             (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+      if (weight) {
+        const float4 w = load4(weight + c0);
+        y.x *= w.x; y.y *= w.y; y.z *= w.z; y.w *= w.w;
+      }
+      if (bias) {
+        const float4 b = load4(bias + c0);
+        y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+      }
+      if (sc) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sc + c0));
+        y.x *= 1.f + a.x; y.y *= 1.f + a.y; y.z *= 1.f + a.z; y.w *= 1.f + a.w;
+      }
+      if (sh) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sh + c0));
+        y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
+      }
+      store4(orow + c0, y);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // WanRMSNorm over the full channel dim + 3-axis RoPE, in place on bf16 [B, L, heads*128].
 //   t4d:378-394: y = bf16(bf16(x * bf16(rstd)) * w), rstd = rsqrt(mean(x^2) + eps) in fp32;
@@ -501,6 +579,14 @@ extern "C" int m4d_layernorm_modulate(const void* x, int x_is_bf16, const void* 
   const bf16* bb = static_cast<const bf16*>(bias);
   const bf16* sgp = static_cast<const bf16*>(sg);
   const bf16* sgg = static_cast<const bf16*>(sg_gate);
+  if (!x_is_bf16 && !out_is_f32 && sgp == nullptr && C <= 128 * 4 * LW_MAXV &&
+      (shift == nullptr || aligned16(shift)) && (scale == nullptr || aligned16(scale))) {
+    layernorm_modulate_wg_kernel<<<static_cast<unsigned>((rows + 1) / 2), 256, 0, stream>>>(
+        static_cast<const float*>(x), w, bb, shift, scale, mod_batch_stride, rows, rows_per_batch, C, eps,
+        static_cast<bf16*>(out));
+    M4D_CHECK_LAUNCH("layernorm_modulate_wg_kernel");
+    return M4D_OK;
+  }
   dim3 grid(static_cast<unsigned>(rows));
 #define LAUNCH_LN(TI, TO)                                                                       \
   layernorm_modulate_kernel<TI, TO><<<grid, ROW_THREADS, 0, stream>>>(                          \
