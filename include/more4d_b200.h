@@ -75,6 +75,18 @@ int m4d_attention_fwd(const void* q, const void* k, const void* v, void* out, in
                       long long out_stride_l, const int* k_lens, float softmax_scale,
                       int accumulate, void* stream);
 
+/* TWO independently normalised attentions over one query set in ONE launch, summed in bf16:
+ *   out = bf16( bf16(softmax(q k[:seg]^T) v[:seg]) + bf16(softmax(q k[seg:]^T) v[seg:]) )
+ * — WanI2VCrossAttention, wan_transformer4d.py:533-552 (text context then CLIP-image context;
+ * bf16 addition commutes, so the order of the two terms is free).  seg_len must be a positive
+ * multiple of 128 and < Lk; bit-identical to m4d_attention_fwd on k[:seg] followed by
+ * m4d_attention_fwd(accumulate=1) on k[seg:]. */
+int m4d_attention_fwd_seg2(const void* q, const void* k, const void* v, void* out, int B, int Lq,
+                           int Lk, int seg_len, int heads, int head_dim, long long q_stride_b,
+                           long long q_stride_l, long long kv_stride_b, long long kv_stride_l,
+                           long long out_stride_b, long long out_stride_l, float softmax_scale,
+                           void* stream);
+
 /* m4d_attention_fwd whose epilogue SCATTERS the query rows over n_out <= 8 output buffers: row l goes
  * to out[l / rows_per_out] (HOST array of DEVICE pointers, possibly peer-GPU memory) at row
  * l % rows_per_out, with the given batch / token strides.  The returning half of the

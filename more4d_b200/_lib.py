@@ -28,6 +28,7 @@ _SIGNATURES = {
     "m4d_gemm_bf16": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _P, _L, _P, _L, _I, _P]),
     "m4d_attention_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P,
                                   _F, _I, _P]),
+    "m4d_attention_fwd_seg2": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _F, _P]),
     "m4d_attention_fwd_scatter": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P,
                                           _F, _P]),
     "m4d_layernorm_modulate": (c_int, [_P, _I, _P, _P, _P, _P, _L, _L, _I, _I, _F, _P, _I, _P, _L,

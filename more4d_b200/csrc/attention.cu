@@ -153,6 +153,13 @@ struct AttnParams {
   const int* k_lens;                      // [B] or null
   float scale_log2;                       // softmax_scale * log2(e)
   int accumulate;                         // out = bf16(out + bf16(o))  (summed cross-attention)
+  // Two independently normalised attentions in ONE launch (WanI2VCrossAttention, t4d:533-552: text
+  // and CLIP-image context, outputs summed in bf16): keys [0, seg_tiles*128) and [seg_tiles*128, Lk)
+  // are separate softmax segments.  At the segment boundary the softmax warps normalise and store
+  // the first segment's O, start over (reference max, row sum, accumulator), and the final
+  // epilogue adds the second segment onto the stored bf16 — one Q load, one prologue, one epilogue
+  // pair instead of two launches that each run 3-4 key tiles.  0 = one segment.
+  int seg_tiles;
   // scatter epilogue (sequence-parallel exchange fused into the attention epilogue): query row l
   // is stored to out_scatter[l / scatter_rows] at row l % scatter_rows — the destinations are
   // the ranks' receive buffers (peer memory), one launch serves all of them
@@ -290,7 +297,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int k4 = 0; k4 < 8 / NS; ++k4) {
               const int kk = sl * (8 / NS) + k4;
               umma_ts(tO0 + t * 128, tS0 + t * 128 + kk * 8, dp(b_lo + kk * (2048 >> 4), HI), idesc_pv,
-                      !(j == 0 && kk == 0));
+                      !((j == 0 || j == p.seg_tiles) && kk == 0));
             }
             // MODE 1: a softmax warp whose SECOND P half needs a new reference must rescale O
             // after these MMAs and before the next ones (rare; nobody waits otherwise)
@@ -562,9 +569,65 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_st_wait();
     };
 
+    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
+    const bool row_ok = q_row < p.Lq;
+    bf16* orow;
+    {
+      bf16* obase = p.out;
+      int o_row = q_row;
+      if (p.scatter_rows > 0 && row_ok) {
+        const int dst = q_row / p.scatter_rows;
+        obase = p.out_scatter[dst];
+        o_row = q_row - dst * p.scatter_rows;
+      }
+      orow = obase + static_cast<long long>(b) * p.out_stride_b +
+             static_cast<long long>(o_row) * p.out_stride_l + head * A_D;
+    }
+    // O / l -> bf16 -> global (accum: out = bf16(bf16(o) + out))
+    auto store_o = [&](float inv_l, bool accum) {
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(tO + cc * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
+            uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
+            if (accum) {
+              const uint4 prev = *dst;
+              const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
+                v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
+              }
+            }
+            uint4 ov;
+            ov.x = pack_bf16(v[0], v[1]);
+            ov.y = pack_bf16(v[2], v[3]);
+            ov.z = pack_bf16(v[4], v[5]);
+            ov.w = pack_bf16(v[6], v[7]);
+            *dst = ov;
+          }
+        }
+      }
+    };
+
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      if (__builtin_expect(j > 0 && j == p.seg_tiles, 0)) {
+        // segment boundary: "S_t(j) ready" implies PV_t(j-1) has finished, so O holds the whole
+        // first segment; the next PV starts a fresh accumulator (MMA warp) — finish this one
+        store_o(1.0f / l_sum, p.accumulate != 0);
+        m_used = -INFINITY;
+        l_sum = 0.f;
+      }
+      const bool first = (j == 0) || (j == p.seg_tiles);   // no reference yet in this segment
       uint32_t s[128];
       uint32_t ph[32];
       const int valid = kv_len - j * A_BKV;        // keys of this tile that exist
@@ -594,10 +657,10 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (i >= valid) s[i] = 0xFF800000u;
         }
         exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
-        if (__builtin_expect(__any_sync(0xffffffffu, (j == 0) || !(l0 + l1 < A_SUM_GUARD)), 0)) {
+        if (__builtin_expect(__any_sync(0xffffffffu, first || !(l0 + l1 < A_SUM_GUARD)), 0)) {
           // exact path for the whole tile: S is intact (nothing of this tile has been stored);
           // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled
-          const bool mine = (j == 0) || !(l0 + l1 < A_SUM_GUARD);
+          const bool mine = first || !(l0 + l1 < A_SUM_GUARD);
           float mxr = -INFINITY;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -609,11 +672,11 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           float f = 1.0f;
           if (mine) {
             const float m_new = fmaxf(m_used, mxr);
-            f = (j == 0) ? 0.f : fast_exp2((m_used - m_new) * c);
+            f = first ? 0.f : fast_exp2((m_used - m_new) * c);
             m_used = m_new;
             l_sum *= f;
           }
-          if (j > 0) rescale_o(f);                 // warp-collective tcgen05 ops: every lane takes part
+          if (!first) rescale_o(f);                // warp-collective tcgen05 ops: every lane takes part
           neg_mc = -m_used * c;
           tmem_ld32(tS + 0, s + 0);
           tmem_ld32(tS + 32, s + 32);
@@ -705,7 +768,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
         }
         const float mxr = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        if (j == 0) {
+        if (first) {
           m_used = mxr;
         } else {
           const float m_new = fmaxf(m_used, mxr);
@@ -735,48 +798,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ---- epilogue: O / l -> bf16 -> global
     mbar_wait(&o_final[t], 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
-    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
-    const bool row_ok = q_row < p.Lq;
-    bf16* obase = p.out;
-    int o_row = q_row;
-    if (p.scatter_rows > 0 && row_ok) {
-      const int dst = q_row / p.scatter_rows;
-      obase = p.out_scatter[dst];
-      o_row = q_row - dst * p.scatter_rows;
-    }
-    bf16* orow = obase + static_cast<long long>(b) * p.out_stride_b +
-                 static_cast<long long>(o_row) * p.out_stride_l + head * A_D;
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t o[32];
-      tmem_ld32(tO + cc * 32, o);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
-          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
-          if (p.accumulate) {
-            const uint4 prev = *dst;
-            const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
-              v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
-            }
-          }
-          uint4 ov;
-          ov.x = pack_bf16(v[0], v[1]);
-          ov.y = pack_bf16(v[2], v[3]);
-          ov.z = pack_bf16(v[4], v[5]);
-          ov.w = pack_bf16(v[6], v[7]);
-          *dst = ov;
-        }
-      }
-    }
+    store_o(1.0f / l_sum, p.accumulate != 0 || p.seg_tiles > 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -792,7 +814,7 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
                           long long q_stride_l, long long kv_stride_b, long long kv_stride_l,
                           long long out_stride_b, long long out_stride_l, const int* k_lens,
                           float softmax_scale, int accumulate, void* const* out_scatter, int n_scatter,
-                          int scatter_rows, void* stream_) {
+                          int scatter_rows, int seg_len, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scatter > 0) {
     M4D_REQUIRE(out_scatter && n_scatter <= 8 && scatter_rows > 0 &&
@@ -804,6 +826,8 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
   M4D_REQUIRE(q && k && v && out, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(head_dim == A_D, M4D_ERR_UNSUPPORTED);          // d = 128 is the Wan2.1 invariant
+  M4D_REQUIRE(seg_len >= 0 && seg_len % A_BKV == 0 && seg_len < Lk && (seg_len == 0 || (k_lens == nullptr && n_scatter == 0)),
+              M4D_ERR_UNSUPPORTED);
   M4D_REQUIRE(heads <= 65535 && B <= 65535, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(q_stride_l >= heads * A_D && kv_stride_l >= heads * A_D &&
                   out_stride_l >= heads * A_D,
@@ -863,6 +887,7 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
   p.scale_log2 = (softmax_scale > 0.f ? softmax_scale : 1.0f / sqrtf(static_cast<float>(A_D))) *
                  1.4426950408889634f;
   p.accumulate = accumulate;
+  p.seg_tiles = seg_len / A_BKV;
   p.scatter_rows = n_scatter > 0 ? scatter_rows : 0;
   for (int i = 0; i < 8; ++i) p.out_scatter[i] = i < n_scatter ? static_cast<bf16*>(out_scatter[i]) : nullptr;
   dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
@@ -878,7 +903,18 @@ extern "C" int m4d_attention_fwd(const void* q, const void* k, const void* v, vo
                                  float softmax_scale, int accumulate, void* stream_) {
   return attention_impl(q, k, v, out, B, Lq, Lk, heads, head_dim, q_stride_b, q_stride_l, kv_stride_b,
                         kv_stride_l, out_stride_b, out_stride_l, k_lens, softmax_scale, accumulate, nullptr,
-                        0, 0, stream_);
+                        0, 0, 0, stream_);
+}
+
+extern "C" int m4d_attention_fwd_seg2(const void* q, const void* k, const void* v, void* out, int B, int Lq,
+                                      int Lk, int seg_len, int heads, int head_dim, long long q_stride_b,
+                                      long long q_stride_l, long long kv_stride_b, long long kv_stride_l,
+                                      long long out_stride_b, long long out_stride_l, float softmax_scale,
+                                      void* stream_) {
+  M4D_REQUIRE(seg_len > 0, M4D_ERR_BAD_SHAPE);
+  return attention_impl(q, k, v, out, B, Lq, Lk, heads, head_dim, q_stride_b, q_stride_l, kv_stride_b,
+                        kv_stride_l, out_stride_b, out_stride_l, nullptr, softmax_scale, 0, nullptr, 0, 0,
+                        seg_len, stream_);
 }
 
 extern "C" int m4d_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* out, int n_out,
@@ -888,6 +924,6 @@ extern "C" int m4d_attention_fwd_scatter(const void* q, const void* k, const voi
                                          const int* k_lens, float softmax_scale, void* stream_) {
   return attention_impl(q, k, v, nullptr, B, Lq, Lk, heads, head_dim, q_stride_b, q_stride_l, kv_stride_b,
                         kv_stride_l, out_stride_b, out_stride_l, k_lens, softmax_scale, 0, out, n_out,
-                        rows_per_out, stream_);
+                        rows_per_out, 0, stream_);
 }
 

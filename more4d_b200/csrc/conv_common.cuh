@@ -39,9 +39,6 @@ struct ConvParams {
   int vec_ok;               // NHWC rows, bias and residual allow 16-byte vector access per 32 channels
 };
 
-// SiLU on a bf16-rounded input, result rounded to bf16 (reference: nn.SiLU on a bf16 tensor).
-// __fdividef / __expf: the <= 2 ulp fp32 error is invisible after the bf16 rounding.
-__device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(__fdividef(x, 1.f + __expf(-x))); }
 
 __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
   f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
@@ -85,6 +82,41 @@ __device__ __forceinline__ void conv_chunk_values(const uint32_t* rr, const bf16
       for (int e = 0; e < 8; ++e) v[q * 8 + e] = bf16_round(v[q * 8 + e] + r8[e]);
     }
   }
+}
+
+// Packed form of conv_chunk_values: 16 words of two bf16 channels each.  bias add in fp32 and one
+// rounding (the bf16 conv output), residual add as add.rn.bf16x2 (== fp32 add + rounding).
+__device__ __forceinline__ void conv_chunk_packed(const uint32_t* rr, const bf16* bias, const uint4* res4,
+                                                  uint32_t* y) {
+  if (bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(bias) + q);
+      const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        y[q * 4 + e] = pack_bf16(__uint_as_float(rr[q * 8 + 2 * e]) + bf16_lo(bw[e]),
+                                 __uint_as_float(rr[q * 8 + 2 * e + 1]) + bf16_hi(bw[e]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = pack_bf16(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
+  }
+  if (res4 != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      y[q * 4 + 0] = add_bf16x2(y[q * 4 + 0], res4[q].x);
+      y[q * 4 + 1] = add_bf16x2(y[q * 4 + 1], res4[q].y);
+      y[q * 4 + 2] = add_bf16x2(y[q * 4 + 2], res4[q].z);
+      y[q * 4 + 3] = add_bf16x2(y[q * 4 + 3], res4[q].w);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_chunk_packed(bf16* o, const uint32_t* y) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    reinterpret_cast<uint4*>(o)[q] = make_uint4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
 }
 
 __device__ __forceinline__ void store_chunk_bf16(bf16* o, const float* v) {

@@ -66,32 +66,47 @@ __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_l
 // bf16, then y / norm, * sqrt(C), * gamma, SiLU each rounded to bf16.  Writes the raw output
 // (when p.out != null) and the normalised one; removes one read + one write of the activation
 // and a kernel launch per RMS_norm.
+//
+// Two passes so that the accumulators can be handed back EARLY: pass 1 drains TMEM (bias,
+// rounding, residual, raw store, sum of squares) into packed bf16 registers; the caller then
+// releases the TMEM buffer and pass 2 (the normalisation: 2/3 of the epilogue's instructions)
+// runs while the tensor pipe is already on the next tile.  At NT = 192 the accumulators are
+// single-buffered (2 sub-tiles x 192 columns x 2 > 512), so everything before the release is
+// exposed: 7.4 ms of a 23.6 ms launch at 49x360x640 before the split (profiles/conv_fused_r02.md).
+// TMEM loads are double-buffered (chunk c+1 is in flight while chunk c is processed; the
+// single-buffered version spent 40 % of its samples on the TMEM / residual scoreboards), all
+// bf16 arithmetic is packed (ptx.cuh), and the epilogue warps run with 224 registers
+// (setmaxnreg) to hold 96 packed words + two 32-word TMEM chunks + two residual chunks.
 template <int NTC>
-__device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t_row, long long pix_off,
-                                                 bool pix_ok, uint4* rnext) {
-  uint32_t yp[NTC / 2];
+__device__ __forceinline__ float rmsnorm_pass1(const ConvParams& p, uint32_t t_row, long long pix_off,
+                                               bool pix_ok, uint4* rnext, uint32_t* yp) {
   float ss = 0.f;
   const bool has_res = p.residual != nullptr && pix_ok;
+  uint32_t rr[2][32];
+  tmem_ld32(t_row, rr[0]);
 #pragma unroll
   for (int c0 = 0; c0 < NTC; c0 += 32) {
+    const int cur = (c0 >> 5) & 1;
     uint4 rcur[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
     if (has_res && c0 + 32 < NTC) load_res_chunk(p.residual + pix_off + c0 + 32, rnext);   // one chunk ahead
-    uint32_t rr[32];
-    tmem_ld32(t_row + c0, rr);
     tmem_ld_wait();
-    float v[32];
-    const long long off = pix_off + c0;
-    conv_chunk_values(rr, p.bias ? p.bias + c0 : nullptr, has_res ? rcur : nullptr, v);
-    if (p.out != nullptr && pix_ok) store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + off, v);
+    if (c0 + 32 < NTC) tmem_ld32(t_row + c0 + 32, rr[cur ^ 1]);
+    uint32_t* y = yp + (c0 >> 1);
+    conv_chunk_packed(rr[cur], p.bias ? p.bias + c0 : nullptr, has_res ? rcur : nullptr, y);
+    if (p.out != nullptr && pix_ok) store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, y);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      ss += v[i] * v[i] + v[i + 1] * v[i + 1];
-      yp[(c0 + i) >> 1] = pack_bf16(v[i], v[i + 1]);
+    for (int i = 0; i < 16; ++i) {
+      const float a = bf16_lo(y[i]), b = bf16_hi(y[i]);
+      ss += a * a + b * b;
     }
   }
-  if (!pix_ok) return;
+  return ss;
+}
+
+template <int NTC>
+__device__ __forceinline__ void rmsnorm_pass2(const ConvParams& p, long long pix_off, const uint32_t* yp, float ss) {
   const float inv = 1.0f / fmaxf(bf16_round(sqrtf(ss)), 1e-12f);
   const float sc = sqrtf(static_cast<float>(NTC));
   bf16* o = p.norm_out + pix_off;
@@ -102,19 +117,23 @@ __device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t
     uint32_t ow[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const uint32_t yw = yp[(c0 >> 1) + e];
-      float a = __uint_as_float(yw << 16), b = __uint_as_float(yw & 0xFFFF0000u);
-      const float ga = __uint_as_float(gw[e] << 16), gb = __uint_as_float(gw[e] & 0xFFFF0000u);
-      a = bf16_round(bf16_round(bf16_round(a * inv) * sc) * ga);
-      b = bf16_round(bf16_round(bf16_round(b * inv) * sc) * gb);
-      if (p.norm_silu) {
-        a = silu_bf16r(a);
-        b = silu_bf16r(b);
-      }
-      ow[e] = pack_bf16(a, b);
+      ow[e] = rmsnorm_tail_bf16x2(yp[(c0 >> 1) + e], inv, sc, gw[e]);
+      if (p.norm_silu) ow[e] = silu_bf16x2(ow[e]);
     }
     *reinterpret_cast<uint4*>(o + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
+}
+
+// One tile of the fused epilogue: pass 1, release the accumulators, pass 2.
+template <int NTC>
+__device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t_row, long long pix_off,
+                                                 bool pix_ok, uint4* rnext, uint64_t* tempty_bar, int lane) {
+  uint32_t yp[NTC / 2];
+  const float ss = rmsnorm_pass1<NTC>(p, t_row, pix_off, pix_ok, rnext, yp);
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty_bar);
+  if (pix_ok) rmsnorm_pass2<NTC>(p, pix_off, yp, ss);
 }
 
 // The nine spatial taps of one (time tap, 64-channel block): wait for each weight stage, issue,
@@ -213,8 +232,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int tiles = p.T_out * tiles_h * tiles_w * p.n_tiles;
   const int cblocks = (p.Cin + 63) / 64;
 
+  // register split (setmaxnreg, issued inside each role's branch so that ptxas budgets the
+  // branch with it): producers / issuer / allocator 80, epilogue warps 208
   if (warp == 0) {
     // ------------------------------------------------------------ halo producer
+    reg_dec<80>();
     if (lane == 0) {
       int sa = 0;
       uint32_t pa = 0;
@@ -238,6 +260,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------ weight producer
+    reg_dec<80>();
     if (lane == 0) {
       uint32_t blk = 0;                                // running (time tap, channel block) counter
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -267,6 +290,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // what bounded the kernel (profiles/conv_halo_r01.md: tensor pipe 56 % at N = 96, 75 % at
     // N = 192 with ~250 clocks of bookkeeping per stage), hence: static ring slots / parities
     // (BST), and the NEXT stage's barrier is probed before the current stage's MMAs are issued.
+    reg_dec<80>();
     const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
@@ -307,8 +331,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       if (elect_one()) umma_commit(&tfull[acc]);
     }
-  } else if (warp >= 4) {
+  } else if (warp == 2) {
+    reg_dec<80>();
+  } else {
     // ------------------------------------------------------------ epilogue
+    reg_inc<208>();
     const int sub = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
@@ -346,8 +373,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              acc * 2 * p.acc_stride + sub * p.acc_stride;
       if (p.norm_out != nullptr) {                     // NT == Cout in {96, 192}, checked on the host
-        if (p.NT == 96) epilogue_rmsnorm<96>(p, t_row, pix_off, pix_ok, rnext);
-        else epilogue_rmsnorm<192>(p, t_row, pix_off, pix_ok, rnext);
+        if (p.NT == 96) epilogue_rmsnorm<96>(p, t_row, pix_off, pix_ok, rnext, &tempty[acc], lane);
+        else epilogue_rmsnorm<192>(p, t_row, pix_off, pix_ok, rnext, &tempty[acc], lane);
+        continue;                                      // the accumulators were released after pass 1
       } else {
         for (int c0 = 0; c0 < p.NT; c0 += 32) {
           const int n0 = n_blk * p.NT + c0;
@@ -361,9 +389,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld_wait();
           if (!pix_ok) continue;
           if (p.vec_ok && n0 + 32 <= p.Cout) {
-            float v[32];
-            conv_chunk_values(rr, p.bias ? p.bias + n0 : nullptr, vec_res ? rcur : nullptr, v);
-            store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + pix_off + c0, v);
+            uint32_t y[16];
+            conv_chunk_packed(rr, p.bias ? p.bias + n0 : nullptr, vec_res ? rcur : nullptr, y);
+            store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, y);
           } else {
             conv_store_chunk_slow(p, rr, t, h, w, n0);
           }

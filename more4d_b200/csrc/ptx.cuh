@@ -254,6 +254,38 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
+// ---- packed bf16x2 arithmetic for the bf16-faithful row math (every intermediate of the
+// reference's bf16 tensors is rounded to bf16).  A product of two bf16 values is exact in fp32, and a
+// sum is exact whenever the smaller operand can still move the rounding, so mul/add.rn.bf16x2
+// equal "fp32 op, then round to bf16" — one instruction for two
+// elements instead of six (two fp32 ops, two conversions, two shifts back).
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+// bf16( x / (1 + exp(-x)) ) of both halves: nn.SiLU on a bf16 tensor (fp32 inside, one rounding)
+__device__ __forceinline__ uint32_t silu_bf16x2(uint32_t w) {
+  const float a = bf16_lo(w), b = bf16_hi(w);
+  return pack_bf16(__fdividef(a, 1.f + __expf(-a)), __fdividef(b, 1.f + __expf(-b)));
+}
+// bf16( 1 / (1 + exp(-x)) ) of both halves: torch.sigmoid on a bf16 tensor
+__device__ __forceinline__ uint32_t sigmoid_bf16x2(uint32_t w) {
+  const float a = bf16_lo(w), b = bf16_hi(w);
+  return pack_bf16(__fdividef(1.f, 1.f + __expf(-a)), __fdividef(1.f, 1.f + __expf(-b)));
+}
+// RMS_norm tail on a packed pair (wan_vae.py:43-58): bf16(bf16(bf16(y * inv) * sc) * gamma)
+__device__ __forceinline__ uint32_t rmsnorm_tail_bf16x2(uint32_t yw, float inv, float sc, uint32_t gw) {
+  const uint32_t t = pack_bf16(bf16_lo(yw) * inv, bf16_hi(yw) * inv);
+  return mul_bf16x2(pack_bf16(bf16_lo(t) * sc, bf16_hi(t) * sc), gw);
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

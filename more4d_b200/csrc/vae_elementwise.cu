@@ -24,9 +24,6 @@ __device__ __forceinline__ float wsum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// fast division: these passes were instruction-bound on IEEE divides, not HBM-bound; the
-// results are re-rounded to bf16 (2^-9) so the <= 2 ulp fp32 error of __fdividef is invisible
-__device__ __forceinline__ float silu_bf16r(float x) { return bf16_round(__fdividef(x, 1.f + __expf(-x))); }
 
 // RMS_norm (wan_vae.py:43-58: F.normalize over channels * sqrt(C) * gamma) [+ SiLU].
 // Every thread owns one 16-byte vector (8 channels) of a pixel, so a pixel is shared by
@@ -80,15 +77,8 @@ rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamm
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
-      const float ga = __uint_as_float(gw[e] << 16), gb = __uint_as_float(gw[e] & 0xFFFF0000u);
-      a = bf16_round(bf16_round(bf16_round(a * inv) * sc) * ga);
-      b = bf16_round(bf16_round(bf16_round(b * inv) * sc) * gb);
-      if (do_silu) {
-        a = silu_bf16r(a);
-        b = silu_bf16r(b);
-      }
-      o[e] = pack_bf16(a, b);
+      o[e] = rmsnorm_tail_bf16x2(w[e], inv, sc, gw[e]);
+      if (do_silu) o[e] = silu_bf16x2(o[e]);
     }
     *reinterpret_cast<uint4*>(out + pix * C + lv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -240,11 +230,9 @@ groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ sta
       for (int e = 0; e < 4; ++e) {
         const float2 A = *reinterpret_cast<const float2*>(&ab[c0 + 2 * e]);
         const float2 B = *reinterpret_cast<const float2*>(&ab[C + c0 + 2 * e]);
-        float a0 = bf16_round(fmaf(__uint_as_float(xs[e] << 16), A.x, B.x));
-        float a1 = bf16_round(fmaf(__uint_as_float(xs[e] & 0xFFFF0000u), A.y, B.y));
-        a0 *= bf16_round(__fdividef(1.f, 1.f + __expf(-a0)));
-        a1 *= bf16_round(__fdividef(1.f, 1.f + __expf(-a1)));
-        o[e] = pack_bf16(a0, a1);
+        // y = bf16(x * A + B); swish = bf16(y * bf16(sigmoid(y)))   (x * torch.sigmoid(x) on bf16 tensors)
+        const uint32_t y = pack_bf16(fmaf(bf16_lo(xs[e]), A.x, B.x), fmaf(bf16_hi(xs[e]), A.y, B.y));
+        o[e] = mul_bf16x2(y, sigmoid_bf16x2(y));
       }
       __stcs(of + i, make_uint4(o[0], o[1], o[2], o[3]));
     }

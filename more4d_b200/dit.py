@@ -291,7 +291,20 @@ class WanI2VCrossAttention(WanSelfAttention):
             ki = ops.linear(ctx_img, self.k_img.weight, self.k_img.bias)
             ops.rmsnorm_rope_(ki, self.norm_k_img.weight if self.qk_norm else None, n, self.eps)
             vi = ops.linear(ctx_img, self.v_img.weight, self.v_img.bias)
+            if k.shape[1] % 128 == 0:
+                # text keys then image keys in ONE buffer (views returned), so `attend` can run both
+                # softmaxes in one launch (ops.attention_seg2)
+                Lt = k.shape[1]
+                kc, vc = torch.cat([k, ki], dim=1), torch.cat([v, vi], dim=1)
+                k, ki, v, vi = kc[:, :Lt], kc[:, Lt:], vc[:, :Lt], vc[:, Lt:]
         return k, v, ki, vi
+
+    @staticmethod
+    def _adjacent(a: Tensor, b: Tensor) -> bool:
+        """b's rows start where a's end, inside one [B, La + Lb, C] buffer."""
+        return (a.stride() == b.stride() and a.stride(1) == a.shape[2] and a.shape[1] % 128 == 0 and
+                b.data_ptr() == a.data_ptr() + a.shape[1] * a.stride(1) * a.element_size() and
+                (a.shape[0] == 1 or a.stride(0) == (a.shape[1] + b.shape[1]) * a.stride(1)))
 
     def attend(self, x: Tensor, context: Optional[Tensor], kv=None) -> Tensor:   # type: ignore[override]
         B, L, C = x.shape
@@ -300,6 +313,11 @@ class WanI2VCrossAttention(WanSelfAttention):
         ops.rmsnorm_rope_(q, self.norm_q.weight if self.qk_norm else None, n, self.eps)
         k, v, ki, vi = kv if kv is not None else self.project_context(context)
         q4 = q.view(B, L, n, d)
+        if ki is not None and self._adjacent(k, ki) and self._adjacent(v, vi):
+            Lt, Lc = k.shape[1], k.shape[1] + ki.shape[1]
+            kc = k.as_strided((B, Lc, n, d), (k.stride(0), k.stride(1), d, 1))
+            vc = v.as_strided((B, Lc, n, d), (v.stride(0), v.stride(1), d, 1))
+            return ops.attention_seg2(q4, kc, vc, Lt).view(B, L, C)
         o = ops.attention(q4, k.view(B, -1, n, d), v.view(B, -1, n, d))
         if ki is not None:
             ops.attention(q4, ki.view(B, -1, n, d), vi.view(B, -1, n, d), out=o, accumulate=True)

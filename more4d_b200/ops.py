@@ -155,6 +155,35 @@ def attention(q: Tensor, k: Tensor, v: Tensor, k_lens: Optional[Tensor] = None,
     return out
 
 
+def attention_seg2(q: Tensor, k: Tensor, v: Tensor, seg_len: int,
+                   softmax_scale: Optional[float] = None, out: Optional[Tensor] = None) -> Tensor:
+    """attention(q, k[:, :seg_len], v[:, :seg_len]) + attention(q, k[:, seg_len:], v[:, seg_len:]) (each
+    rounded to bf16, summed in bf16) in ONE launch — the image+text cross-attention, t4d:533-552.
+    seg_len: positive multiple of 128, < Lk."""
+    _lib.require_device()
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _req(t, BF16, n)
+        if t.dim() != 4 or t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+            raise ValueError(f"more4d_b200.attention_seg2: `{n}` must be [B, L, N, D] with contiguous (N, D)")
+    B, Lq, N, D = q.shape
+    Lk = k.shape[1]
+    if k.shape != v.shape or k.stride() != v.stride() or k.shape[0] != B or k.shape[2] != N or k.shape[3] != D:
+        raise ValueError("more4d_b200.attention_seg2: q/k/v shape or stride mismatch")
+    if seg_len <= 0 or seg_len % 128 or seg_len >= Lk:
+        raise ValueError("more4d_b200.attention_seg2: seg_len must be a positive multiple of 128 below Lk")
+    if out is None:
+        out = torch.empty(B, Lq, N, D, device=q.device, dtype=BF16)
+    _req(out, BF16, "out")
+    ev = _t0("cross_attention")
+    rc = _lib.lib().m4d_attention_fwd_seg2(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Lq, Lk, seg_len, N, D,
+        q.stride(0), q.stride(1), k.stride(0), k.stride(1), out.stride(0), out.stride(1),
+        float(softmax_scale) if softmax_scale else 0.0, _stream())
+    _lib.check(rc, "m4d_attention_fwd_seg2")
+    _t1("cross_attention", ev, 4.0 * B * N * Lq * Lk * D)
+    return out
+
+
 def attention_scatter(q: Tensor, k: Tensor, v: Tensor, outs, k_lens: Optional[Tensor] = None) -> None:
     """attention(q, k, v) with query rows scattered over `outs`: rows [i*R, (i+1)*R) go to outs[i]
     ([B, R, N, 128] views with equal strides — typically peer GPUs' buffers), one launch."""

@@ -218,6 +218,29 @@ def test_attention_strided_views_and_accumulate(ops):
     assert rel_err(out.float().cpu(), ref2) < 6e-3
 
 
+@pytest.mark.parametrize("B,Lq,seg,Lk", [(2, 300, 512, 769), (1, 513, 128, 129), (1, 90, 256, 512)])
+def test_attention_two_segments_one_launch(ops, B, Lq, seg, Lk):
+    """m4d_attention_fwd_seg2 (text + image cross-attention in one launch, t4d:533-552) is
+    BIT-IDENTICAL to the two-launch form (attention, then attention(accumulate=True)) and matches
+    the oracle's sum of two separately normalised attentions."""
+    N = 2
+    q = _rand((B, Lq, N, 128), 61)
+    k = _rand((B, Lk, N, 128), 62)
+    v = _rand((B, Lk, N, 128), 63)
+    k[0, Lk - 1, 0] = (q[0, 7, 0].float() * 6.0).to(BF16)         # second segment far above the first
+    k[0, 5, 1] = (q[0, 9, 1].float() * 6.0).to(BF16)              # and the other way round
+    ar = O.Arith(True)
+    ref = ar.r(O.attention(q, k[:, :seg], v[:, :seg], None, ar) + O.attention(q, k[:, seg:], v[:, seg:], None, ar))
+    qg, kg, vg = q.cuda(), k.cuda(), v.cuda()
+    one = ops.attention_seg2(qg, kg, vg, seg)
+    two = ops.attention(qg, kg[:, :seg], vg[:, :seg])
+    ops.attention(qg, kg[:, seg:], vg[:, seg:], out=two, accumulate=True)
+    assert torch.equal(one, two)
+    assert rel_err(one.float().cpu(), ref) < 6e-3
+    with pytest.raises(ValueError):
+        ops.attention_seg2(qg, kg, vg, seg + 1)
+
+
 def test_attention_rejects_head_dim(ops):
     q = _rand((1, 64, 2, 64), 1).cuda()
     with pytest.raises(RuntimeError):

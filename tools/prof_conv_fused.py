@@ -11,7 +11,9 @@ from more4d_b200 import ops           # noqa: E402
 BF16 = torch.bfloat16
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    T, H, W, C = 4, 720, 1280, 96
+    C = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+    T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    H, W = (720, 1280) if C == 96 else (360, 640)
     x = torch.randn(T, H, W, C, device="cuda", dtype=BF16)
     res = torch.randn(T, H, W, C, device="cuda", dtype=BF16)
     w = torch.randn(C, C, 3, 3, 3, device="cuda", dtype=BF16) * 0.02
