@@ -47,17 +47,28 @@ __device__ __forceinline__ uint64_t desc_pair(uint32_t lo, uint32_t hi) {
 }
 
 // All MMAs of one spatial tap: both sub-tiles x KS k-slices of 16 channels.
-template <int KS>
+template <bool PAIR>
+__device__ __forceinline__ void umma_ss_x(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma_ss_2sm(d, a, b, idesc, acc);
+  else umma_ss(d, a, b, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_x(uint64_t* bar) {
+  if (PAIR) umma_commit_2sm(bar);          // arrives on this barrier in BOTH CTAs of the pair
+  else umma_commit(bar);
+}
+
+template <int KS, bool PAIR>
 __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b_lo,
                                           uint32_t idesc, uint32_t acc0) {
 #pragma unroll
   for (int k = 0; k < KS; ++k)
-    umma_ss(d0, desc_pair(a_lo + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc,
-            k == 0 ? acc0 : 1u);
+    umma_ss_x<PAIR>(d0, desc_pair(a_lo + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc,
+                    k == 0 ? acc0 : 1u);
 #pragma unroll
   for (int k = 0; k < KS; ++k)
-    umma_ss(d1, desc_pair(a_lo + 64 + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc,
-            k == 0 ? acc0 : 1u);
+    umma_ss_x<PAIR>(d1, desc_pair(a_lo + 64 + 2 * k, CH_DESC_HI_A), desc_pair(b_lo + 2 * k, CH_DESC_HI_B), idesc,
+                    k == 0 ? acc0 : 1u);
 }
 
 // Epilogue with the NEXT layer's RMS_norm (+ SiLU) fused in (wan_vae.py:43-58 after :198-202):
@@ -77,11 +88,10 @@ __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_l
 // single-buffered version spent 40 % of its samples on the TMEM / residual scoreboards), all
 // bf16 arithmetic is packed (ptx.cuh), and the epilogue warps run with 224 registers
 // (setmaxnreg) to hold 96 packed words + two 32-word TMEM chunks + two residual chunks.
-template <int NTC>
-__device__ __forceinline__ float rmsnorm_pass1(const ConvParams& p, uint32_t t_row, long long pix_off,
-                                               bool pix_ok, uint4* rnext, uint32_t* yp) {
+template <int NTC, bool NORM>
+__device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row, long long pix_off, int n0,
+                                             bool pix_ok, bool has_res, uint4* rnext, uint32_t* yp) {
   float ss = 0.f;
-  const bool has_res = p.residual != nullptr && pix_ok;
   uint32_t rr[2][32];
   tmem_ld32(t_row, rr[0]);
 #pragma unroll
@@ -94,12 +104,14 @@ __device__ __forceinline__ float rmsnorm_pass1(const ConvParams& p, uint32_t t_r
     tmem_ld_wait();
     if (c0 + 32 < NTC) tmem_ld32(t_row + c0 + 32, rr[cur ^ 1]);
     uint32_t* y = yp + (c0 >> 1);
-    conv_chunk_packed(rr[cur], p.bias ? p.bias + c0 : nullptr, has_res ? rcur : nullptr, y);
-    if (p.out != nullptr && pix_ok) store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, y);
+    conv_chunk_packed(rr[cur], p.bias ? p.bias + n0 + c0 : nullptr, has_res ? rcur : nullptr, y);
+    if (NORM) {
+      if (p.out != nullptr && pix_ok) store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, y);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a = bf16_lo(y[i]), b = bf16_hi(y[i]);
-      ss += a * a + b * b;
+      for (int i = 0; i < 16; ++i) {
+        const float a = bf16_lo(y[i]), b = bf16_hi(y[i]);
+        ss += a * a + b * b;
+      }
     }
   }
   return ss;
@@ -124,22 +136,31 @@ __device__ __forceinline__ void rmsnorm_pass2(const ConvParams& p, long long pix
   }
 }
 
-// One tile of the fused epilogue: pass 1, release the accumulators, pass 2.
-template <int NTC>
-__device__ __forceinline__ void epilogue_rmsnorm(const ConvParams& p, uint32_t t_row, long long pix_off,
-                                                 bool pix_ok, uint4* rnext, uint64_t* tempty_bar, int lane) {
+// One tile of the vector epilogue: pass 1, release the accumulators, pass 2 (NORM: the fused
+// RMS_norm; otherwise just the stores of the full NTC-channel row).
+template <int NTC, bool NORM, typename Release>
+__device__ __forceinline__ void epilogue_vec(const ConvParams& p, uint32_t t_row, long long pix_off, int n0,
+                                             bool pix_ok, bool has_res, uint4* rnext, Release& release, int acc,
+                                             int lane) {
   uint32_t yp[NTC / 2];
-  const float ss = rmsnorm_pass1<NTC>(p, t_row, pix_off, pix_ok, rnext, yp);
+  const float ss = drain_pass1<NTC, NORM>(p, t_row, pix_off, n0, pix_ok, has_res, rnext, yp);
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(tempty_bar);
-  if (pix_ok) rmsnorm_pass2<NTC>(p, pix_off, yp, ss);
+  if (lane == 0) release(acc);
+  if (!pix_ok) return;
+  if (NORM) {
+    rmsnorm_pass2<NTC>(p, pix_off, yp, ss);
+  } else {
+#pragma unroll
+    for (int c0 = 0; c0 < NTC; c0 += 32)
+      store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, yp + (c0 >> 1));
+  }
 }
 
 // The nine spatial taps of one (time tap, 64-channel block): wait for each weight stage, issue,
 // release it.  Ring slot and parity are compile-time functions of the tap; the next stage's
 // barrier is probed before the current stage's MMAs are issued so its latency is hidden.
-template <int BST, int KS, int TPB>
+template <int BST, int KS, int TPB, bool PAIR>
 __device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, uint64_t* a_empty_bar,
                                           uint32_t blk, uint32_t a_lo, uint32_t b_lo0, uint32_t b_step,
                                           uint32_t d0, uint32_t d1, uint32_t idesc, bool first_block,
@@ -156,7 +177,7 @@ __device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, u
     if (elect_one()) {
       if (TPB == 1) {
         const uint32_t a_tap = a_lo + ((g / 3) * CH_HW + (g % 3)) * 8;
-        issue_tap<KS>(d0, d1, a_tap, b_lo, idesc, (first_block && g == 0) ? 0u : 1u);
+        issue_tap<KS, PAIR>(d0, d1, a_tap, b_lo, idesc, (first_block && g == 0) ? 0u : 1u);
       } else {
         // thin input: the box holds TPB taps x KS k-slices; slice q -> tap g*TPB + q/KS
 #pragma unroll
@@ -166,13 +187,13 @@ __device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, u
             const int tap9 = g * TPB + q / KS;
             if (tap9 < 9) {
               const uint32_t a_tap = a_lo + ((tap9 / 3) * CH_HW + (tap9 % 3) + 8 * sub) * 8 + 2 * (q % KS);
-              umma_ss(sub ? d1 : d0, desc_pair(a_tap, CH_DESC_HI_A), desc_pair(b_lo + 2 * q, CH_DESC_HI_B),
-                      idesc, (first_block && g == 0 && q == 0) ? 0u : 1u);
+              umma_ss_x<PAIR>(sub ? d1 : d0, desc_pair(a_tap, CH_DESC_HI_A), desc_pair(b_lo + 2 * q, CH_DESC_HI_B),
+                              idesc, (first_block && g == 0 && q == 0) ? 0u : 1u);
             }
           }
       }
-      umma_commit(&b_empty[sb]);
-      if (g == G - 1) umma_commit(a_empty_bar);
+      umma_commit_x<PAIR>(&b_empty[sb]);
+      if (g == G - 1) umma_commit_x<PAIR>(a_empty_bar);
     }
   }
 }
@@ -185,14 +206,26 @@ __device__ __forceinline__ void mma_block(uint64_t* b_full, uint64_t* b_empty, u
 // inputs and the 16-channel latent): K is tap-major / channel-minor, so ONE 64-wide weight box
 // covers TPB consecutive taps and a block of nine taps needs G = ceil(9 / TPB) weight stages
 // (BST = G) instead of nine half-empty ones; k-slice q of a box belongs to tap g*TPB + q/KS.
-template <int BST, int TPB>
-__global__ void __launch_bounds__(CH_THREADS, 1)
+//
+// PAIR: two CTAs of a cluster (one TPC) work on two spatial tiles with ONE weight stream: every
+// MMA is a tcgen05.mma.cta_group::2 with M = 256 — rows 0-127 are this sub-tile of the leader's
+// window, rows 128-255 the same sub-tile of the peer's window, each read from its own CTA's
+// shared memory into its own TMEM — against a weight stage of which each CTA loads and holds
+// HALF the rows (NT/2).  Per SM that halves the weight bytes coming over the L2->SM fabric (two
+// thirds of the 9.2 TB/s the single-CTA kernel pulled at 96 -> 96 channels, profiles/
+// conv_fused_r02.md) and the B-operand shared-memory reads (the N <= 128 layers were bound by
+// A 4 KB + B N*32 B per 48..64-clock MMA).  Protocol as in gemm2.cu: all TMA loads complete on the
+// LEADER's full barriers (the leader arms them with both CTAs' bytes), the leader's issuer
+// commits with a multicast arrival that frees the stage / publishes the accumulators in both
+// CTAs, and both CTAs' epilogue warps arrive on the leader's tempty.
+template <int BST, int TPB, bool PAIR>
+__global__ void __cluster_dims__(PAIR ? 2 : 1, 1, 1) __launch_bounds__(CH_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int b_bytes = p.NT * 128;
+  const int b_bytes = (PAIR ? p.NT / 2 : p.NT) * 128;     // this CTA's part of one weight stage
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.a_stages * CH_A_STRIDE;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + BST * b_bytes);
@@ -204,6 +237,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
   if (warp == 3 && lane == 0) tma_prefetch_desc(&tmW);
   if (warp == 1 && lane == 0) {
@@ -217,20 +252,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);                  // one arrival per epilogue warp
+      mbar_init(&tempty[i], PAIR ? 16 : 8);      // one arrival per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2sm<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_w = (p.W_out + CH_T - 1) / CH_T;
   const int tiles_h = (p.H_out + CH_T - 1) / CH_T;
-  const int tiles = p.T_out * tiles_h * tiles_w * p.n_tiles;
+  const int n_spatial = p.T_out * tiles_h * tiles_w;
+  // work items: (spatial tile [pair], n_blk), n_blk fastest.  A pair's CTAs take spatial tiles
+  // 2s and 2s+1; an odd tail gives the peer a tile beyond the last frame (TMA zero-fills its
+  // loads, its epilogue stores nothing).
+  const int items = (PAIR ? (n_spatial + 1) / 2 : n_spatial) * p.n_tiles;
+  const int item0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int item_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int cblocks = (p.Cin + 63) / 64;
+  auto decode = [&](int item, int& n_blk, int& w_blk, int& h_blk, int& t) {
+    n_blk = item % p.n_tiles;
+    int r = item / p.n_tiles;
+    if (PAIR) r = r * 2 + static_cast<int>(rank);
+    w_blk = r % tiles_w; r /= tiles_w;
+    h_blk = r % tiles_h;
+    t = r / tiles_h;                                   // >= T_out for the odd tail's peer tile
+  };
 
   // register split (setmaxnreg, issued inside each role's branch so that ptxas budgets the
   // branch with it): producers / issuer / allocator 80, epilogue warps 208
@@ -240,17 +293,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (lane == 0) {
       int sa = 0;
       uint32_t pa = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        int r = tile / p.n_tiles;
-        const int w_blk = r % tiles_w; r /= tiles_w;
-        const int h_blk = r % tiles_h;
-        const int t = r / tiles_h;
+      for (int item = item0; item < items; item += item_step) {
+        int n_blk, w_blk, h_blk, t;
+        decode(item, n_blk, w_blk, h_blk, t);
         for (int a = 0; a < p.kt; ++a)
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(&a_empty[sa], pa ^ 1);
-            mbar_arrive_expect_tx(&a_full[sa], CH_A_BYTES);
-            tma_load_4d(sA + sa * CH_A_STRIDE, &tmX, &a_full[sa], cb * 64, w_blk * CH_T - 1,
-                        h_blk * CH_T - 1, t + a - p.pt);
+            if (PAIR) {
+              // the peer never arrives on `a_full`: its bytes are covered by the leader's
+              // expect_tx (safe: a stage is only refilled after the multicast commit that
+              // followed its MMAs, i.e. after the leader's barrier completed the phase)
+              if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * CH_A_BYTES);
+              tma_load_4d_2sm(sA + sa * CH_A_STRIDE, &tmX, mapa_u32(&a_full[sa], 0), cb * 64,
+                              w_blk * CH_T - 1, h_blk * CH_T - 1, t + a - p.pt);
+            } else {
+              mbar_arrive_expect_tx(&a_full[sa], CH_A_BYTES);
+              tma_load_4d(sA + sa * CH_A_STRIDE, &tmX, &a_full[sa], cb * 64, w_blk * CH_T - 1,
+                          h_blk * CH_T - 1, t + a - p.pt);
+            }
             if (++sa == p.a_stages) {
               sa = 0;
               pa ^= 1;
@@ -263,8 +323,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     reg_dec<80>();
     if (lane == 0) {
       uint32_t blk = 0;                                // running (time tap, channel block) counter
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles;
+      for (int item = item0; item < items; item += item_step) {
+        const int n_blk = item % p.n_tiles;
         for (int a = 0; a < p.kt; ++a)
           for (int cb = 0; cb < cblocks; ++cb, ++blk) {
             constexpr int G = (9 + TPB - 1) / TPB;     // weight stages per block
@@ -274,9 +334,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const int sb = g % BST;
               const uint32_t use = blk * per + g / BST;
               mbar_wait(&b_empty[sb], (use & 1) ^ 1);
-              mbar_arrive_expect_tx(&b_full[sb], b_bytes);
-              tma_load_2d(sB + sb * b_bytes, &tmW, &b_full[sb], (a * 9 + g * TPB) * p.Cin + cb * 64,
-                          n_blk * p.NT);
+              const int k0 = (a * 9 + g * TPB) * p.Cin + cb * 64;
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * b_bytes);
+                tma_load_2d_2sm(sB + sb * b_bytes, &tmW, mapa_u32(&b_full[sb], 0), k0,
+                                n_blk * p.NT + static_cast<int>(rank) * (p.NT / 2));
+              } else {
+                mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                tma_load_2d(sB + sb * b_bytes, &tmW, &b_full[sb], k0, n_blk * p.NT);
+              }
             }
           }
       }
@@ -291,45 +357,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // N = 192 with ~250 clocks of bookkeeping per stage), hence: static ring slots / parities
     // (BST), and the NEXT stage's barrier is probed before the current stage's MMAs are issued.
     reg_dec<80>();
-    const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
-    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-    const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
-    const uint32_t b_step = static_cast<uint32_t>(b_bytes) >> 4;
-    int sa = 0;
-    uint32_t pa = 0, blk = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int acc = it % p.acc_bufs;
-      const uint32_t acc_phase = (it / p.acc_bufs) & 1;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 2 * p.acc_stride;
-      const uint32_t d_tmem1 = d_tmem + p.acc_stride;
-      for (int a = 0; a < p.kt; ++a)
-        for (int cb = 0; cb < cblocks; ++cb, ++blk) {
-          const int ch_left = p.Cin - cb * 64;
-          const int kslices = ch_left >= 64 ? 4 : (ch_left >> 4);
-          constexpr int per = ((9 + TPB - 1) / TPB) / BST;
-          const bool ready = mbar_try_wait(&b_full[0], (blk * per) & 1);
-          mbar_wait(&a_full[sa], pa);
-          const uint32_t a_lo = (((a_base + sa * CH_A_STRIDE) >> 4) & 0x3FFF) | (1u << 16);
-          const bool first = (a | cb) == 0;
-          if (TPB > 1) {
-            mma_block<BST, 4 / TPB, TPB>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready);
-          } else {
-            switch (kslices) {
-              case 4: mma_block<BST, 4, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
-              case 2: mma_block<BST, 2, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
-              case 3: mma_block<BST, 3, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
-              default: mma_block<BST, 1, 1>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.NT, 0, 0);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t b_step = static_cast<uint32_t>(b_bytes) >> 4;
+      int sa = 0;
+      uint32_t pa = 0, blk = 0;
+      int it = 0;
+      for (int item = item0; item < items; item += item_step, ++it) {
+        const int acc = it % p.acc_bufs;
+        const uint32_t acc_phase = (it / p.acc_bufs) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 2 * p.acc_stride;
+        const uint32_t d_tmem1 = d_tmem + p.acc_stride;
+        for (int a = 0; a < p.kt; ++a)
+          for (int cb = 0; cb < cblocks; ++cb, ++blk) {
+            const int ch_left = p.Cin - cb * 64;
+            const int kslices = ch_left >= 64 ? 4 : (ch_left >> 4);
+            constexpr int per = ((9 + TPB - 1) / TPB) / BST;
+            const bool ready = mbar_try_wait(&b_full[0], (blk * per) & 1);
+            mbar_wait(&a_full[sa], pa);
+            const uint32_t a_lo = (((a_base + sa * CH_A_STRIDE) >> 4) & 0x3FFF) | (1u << 16);
+            const bool first = (a | cb) == 0;
+            if (TPB > 1) {
+              mma_block<BST, 4 / TPB, TPB, PAIR>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready);
+            } else {
+              switch (kslices) {
+                case 4: mma_block<BST, 4, 1, PAIR>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+                case 2: mma_block<BST, 2, 1, PAIR>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+                case 3: mma_block<BST, 3, 1, PAIR>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+                default: mma_block<BST, 1, 1, PAIR>(b_full, b_empty, &a_empty[sa], blk, a_lo, b_lo0, b_step, d_tmem, d_tmem1, idesc, first, ready); break;
+              }
+            }
+            if (++sa == p.a_stages) {
+              sa = 0;
+              pa ^= 1;
             }
           }
-          if (++sa == p.a_stages) {
-            sa = 0;
-            pa ^= 1;
-          }
-        }
-      if (elect_one()) umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit_x<PAIR>(&tfull[acc]);
+      }
     }
   } else if (warp == 2) {
     reg_dec<80>();
@@ -339,16 +407,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int sub = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
+    // where this warp's lane 0 reports "accumulators drained": the leader's tempty
+    auto release = [&](int acc) {
+      if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+      else mbar_arrive(&tempty[acc]);
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      int r = tile;
-      const int n_blk = r % p.n_tiles; r /= p.n_tiles;
-      const int w_blk = r % tiles_w; r /= tiles_w;
-      const int h_blk = r % tiles_h;
-      const int t = r / tiles_h;
+    for (int item = item0; item < items; item += item_step, ++it) {
+      int n_blk, w_blk, h_blk, t;
+      decode(item, n_blk, w_blk, h_blk, t);
       const int h = h_blk * CH_T + (m >> 3);
       const int w = w_blk * CH_T + sub * 8 + (m & 7);
-      const bool pix_ok = (h < p.H_out) && (w < p.W_out);
+      const bool pix_ok = (h < p.H_out) && (w < p.W_out) && (t < p.T_out);
       const int acc = it % p.acc_bufs;
       const uint32_t acc_phase = (it / p.acc_bufs) & 1;
       // halo convs never interleave channels into frames (n_split >= Cout, checked on the host):
@@ -372,10 +442,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              acc * 2 * p.acc_stride + sub * p.acc_stride;
+      const int n_base = n_blk * p.NT;
       if (p.norm_out != nullptr) {                     // NT == Cout in {96, 192}, checked on the host
-        if (p.NT == 96) epilogue_rmsnorm<96>(p, t_row, pix_off, pix_ok, rnext, &tempty[acc], lane);
-        else epilogue_rmsnorm<192>(p, t_row, pix_off, pix_ok, rnext, &tempty[acc], lane);
+        if (p.NT == 96) epilogue_vec<96, true>(p, t_row, pix_off, 0, pix_ok, vec_res, rnext, release, acc, lane);
+        else epilogue_vec<192, true>(p, t_row, pix_off, 0, pix_ok, vec_res, rnext, release, acc, lane);
         continue;                                      // the accumulators were released after pass 1
+      } else if (p.out_mode == 0 && p.vec_ok && n_base + p.NT <= p.Cout &&
+                 (p.NT == 96 || p.NT == 128 || p.NT == 192)) {    // warp-uniform
+        // full-width tiles of the plain convs (96 / 128 / 192 / 2 x 192 channels): same drain-release-store
+        if (p.NT == 96) epilogue_vec<96, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
+        else if (p.NT == 128) epilogue_vec<128, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
+        else epilogue_vec<192, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
+        continue;
       } else {
         for (int c0 = 0; c0 < p.NT; c0 += 32) {
           const int n0 = n_blk * p.NT + c0;
@@ -399,12 +477,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) release(acc);
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (PAIR) {
+    cluster_sync_all();                  // no CTA may exit while its peer can still touch its smem / TMEM
+    if (warp == 2) tmem_dealloc_2sm<512>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem_base);
+  }
 }
 
 bool conv_halo_eligible(int Cin, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
@@ -434,10 +517,18 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
                     (p.residual == nullptr || aligned16(p.residual)),
                 M4D_ERR_ALIGN);
   }
-  const int b_bytes = NT * 128;
-  const int fixed = 1024 + 512;                         // alignment slack + barriers
   // thin-input mode: Cin in {16, 32} -> 4 / 2 taps per weight box, ring = stages per block
   const int tpb = (p.Cin == 16) ? 4 : (p.Cin == 32 ? 2 : 1);
+  const long long n_spatial = static_cast<long long>(p.T_out) * ((p.H_out + CH_T - 1) / CH_T) *
+                              ((p.W_out + CH_T - 1) / CH_T);
+  // CTA pairs (cta_group::2, one weight stream per two spatial tiles); thin inputs keep the
+  // single-CTA kernel
+  bool pair = tpb == 1 && NT % 16 == 0 && n_spatial >= 2;
+#ifdef M4D_DEV
+  if (g_dev_flags & 0x4000) pair = false;
+#endif
+  const int b_bytes = (pair ? NT / 2 : NT) * 128;       // per CTA and weight stage
+  const int fixed = 1024 + 512;                         // alignment slack + barriers
   // weight ring: all stages of a block when that leaves room for >= 2 halo stages, else 3
   int bst = (CH_SMEM_MAX - fixed - 9 * b_bytes >= 2 * CH_A_STRIDE) ? 9 : 3;
   if (tpb == 2) bst = 5;
@@ -468,7 +559,7 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
     const long long Ktot = static_cast<long long>(p.kt) * 9 * p.Cin;
     cuuint64_t wdim[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Cout_pad)};
     cuuint64_t wstr[1] = {static_cast<cuuint64_t>(Ktot) * 2};
-    cuuint32_t wbox[2] = {64, static_cast<cuuint32_t>(NT)};
+    cuuint32_t wbox[2] = {64, static_cast<cuuint32_t>(pair ? NT / 2 : NT)};
     cuuint32_t wes[2] = {1, 1};
     r = fn(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), wdim, wstr, wbox, wes,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -480,17 +571,18 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   }
   const int smem_bytes = p.a_stages * CH_A_STRIDE + p.stages * b_bytes + fixed;
   void (*kern)(CUtensorMap, CUtensorMap, ConvParams) =
-      tpb == 4 ? conv_halo_kernel<3, 4> : tpb == 2 ? conv_halo_kernel<5, 2>
-      : bst == 9 ? conv_halo_kernel<9, 1> : conv_halo_kernel<3, 1>;
+      tpb == 4 ? conv_halo_kernel<3, 4, false> : tpb == 2 ? conv_halo_kernel<5, 2, false>
+      : pair ? (bst == 9 ? conv_halo_kernel<9, 1, true> : conv_halo_kernel<3, 1, true>)
+      : bst == 9 ? conv_halo_kernel<9, 1, false> : conv_halo_kernel<3, 1, false>;
   {
     int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX),
                      "cudaFuncSetAttribute(conv_halo)");
     if (rc != M4D_OK) return rc;
   }
-  const long long tiles = static_cast<long long>(p.T_out) * ((p.H_out + CH_T - 1) / CH_T) *
-                          ((p.W_out + CH_T - 1) / CH_T) * p.n_tiles;
-  M4D_REQUIRE(tiles < (1ll << 31), M4D_ERR_BAD_SHAPE);
-  const int grid = tiles < sm_count() ? static_cast<int>(tiles) : sm_count();
+  const long long items = (pair ? (n_spatial + 1) / 2 : n_spatial) * p.n_tiles;
+  M4D_REQUIRE(items < (1ll << 30), M4D_ERR_BAD_SHAPE);
+  const int slots = pair ? sm_count() / 2 : sm_count();          // persistent: one CTA (pair) per SM (pair)
+  const int grid = static_cast<int>(items < slots ? items : slots) * (pair ? 2 : 1);
   kern<<<grid, CH_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
   M4D_CHECK_LAUNCH("conv_halo_kernel");
   return M4D_OK;
