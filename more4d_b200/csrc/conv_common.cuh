@@ -86,11 +86,12 @@ __device__ __forceinline__ void conv_chunk_values(const uint32_t* rr, const bf16
 
 // Packed form of conv_chunk_values: 16 words of two bf16 channels each.  bias add in fp32 and one
 // rounding (the bf16 conv output), residual add as add.rn.bf16x2 (== fp32 add + rounding).
-__device__ __forceinline__ void conv_chunk_packed(const uint32_t* rr, const bf16* bias, const uint4* res4,
-                                                  uint32_t* y) {
+template <int Q>                                         // Q 16-byte groups = 8 * Q channels
+__device__ __forceinline__ void conv_packed(const uint32_t* rr, const bf16* bias, const uint4* res4,
+                                            uint32_t* y) {
   if (bias != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < Q; ++q) {
       const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(bias) + q);
       const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -100,17 +101,22 @@ __device__ __forceinline__ void conv_chunk_packed(const uint32_t* rr, const bf16
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = pack_bf16(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
+    for (int i = 0; i < 4 * Q; ++i) y[i] = pack_bf16(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
   }
   if (res4 != nullptr) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < Q; ++q) {
       y[q * 4 + 0] = add_bf16x2(y[q * 4 + 0], res4[q].x);
       y[q * 4 + 1] = add_bf16x2(y[q * 4 + 1], res4[q].y);
       y[q * 4 + 2] = add_bf16x2(y[q * 4 + 2], res4[q].z);
       y[q * 4 + 3] = add_bf16x2(y[q * 4 + 3], res4[q].w);
     }
   }
+}
+
+__device__ __forceinline__ void conv_chunk_packed(const uint32_t* rr, const bf16* bias, const uint4* res4,
+                                                  uint32_t* y) {
+  conv_packed<4>(rr, bias, res4, y);
 }
 
 __device__ __forceinline__ void store_chunk_packed(bf16* o, const uint32_t* y) {

@@ -92,19 +92,23 @@ template <int NTC, bool NORM>
 __device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row, long long pix_off, int n0,
                                              bool pix_ok, bool has_res, uint4* rnext, uint32_t* yp) {
   float ss = 0.f;
-  uint32_t rr[2][32];
-  tmem_ld32(t_row, rr[0]);
+  uint32_t rr[2][16];                              // TMEM loads in 16-column halves, double-buffered
+  tmem_ld16(t_row, rr[0]);
 #pragma unroll
   for (int c0 = 0; c0 < NTC; c0 += 32) {
-    const int cur = (c0 >> 5) & 1;
     uint4 rcur[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
     if (has_res && c0 + 32 < NTC) load_res_chunk(p.residual + pix_off + c0 + 32, rnext);   // one chunk ahead
-    tmem_ld_wait();
-    if (c0 + 32 < NTC) tmem_ld32(t_row + c0 + 32, rr[cur ^ 1]);
     uint32_t* y = yp + (c0 >> 1);
-    conv_chunk_packed(rr[cur], p.bias ? p.bias + n0 + c0 : nullptr, has_res ? rcur : nullptr, y);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int cc = c0 + hf * 16;
+      const int cur = (cc >> 4) & 1;
+      tmem_ld_wait();
+      if (cc + 16 < NTC) tmem_ld16(t_row + cc + 16, rr[cur ^ 1]);
+      conv_packed<2>(rr[cur], p.bias ? p.bias + n0 + cc : nullptr, has_res ? rcur + 2 * hf : nullptr, y + hf * 8);
+    }
     if (NORM) {
       if (p.out != nullptr && pix_ok) store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, y);
 #pragma unroll
@@ -409,8 +413,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int m = quad * 32 + lane;
     // where this warp's lane 0 reports "accumulators drained": the leader's tempty
     auto release = [&](int acc) {
-      if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
-      else mbar_arrive(&tempty[acc]);
+      if (PAIR && !leader) mbar_arrive_cluster_relaxed(mapa_u32(&tempty[acc], 0));
+      else mbar_arrive_relaxed(&tempty[acc]);
     };
     int it = 0;
     for (int item = item0; item < items; item += item_step, ++it) {

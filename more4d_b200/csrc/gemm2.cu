@@ -254,8 +254,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (leader) mbar_arrive(&tempty[acc]);
-        else mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+        // relaxed: only the TMEM reads (complete after tcgen05.wait::ld) must precede the hand-back;
+        // a release at cluster scope would wait for the epilogue's global stores (MEMBAR.ALL.GPU)
+        if (leader) mbar_arrive_relaxed(&tempty[acc]);
+        else mbar_arrive_cluster_relaxed(mapa_u32(&tempty[acc], 0));
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
