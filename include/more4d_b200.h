@@ -211,6 +211,23 @@ int m4d_planar_to_cl(const void* x, void* out, long long P, int C, int Cpad, con
 int m4d_cl_to_planar(const void* x, void* out, long long P, int C, int n_affine, const float* sub,
                      const float* mul, void* stream);
 
+/* 3x3 Conv2d (per frame, padding 1) over channels-last [T, H, W, Cin] -> [T, H, W, 128] whose epilogue
+ * also produces the per-frame GroupNorm(32) statistics of its (bias / residual-added, bf16-rounded)
+ * output — the input of the next Normalize in the adaptors' ResnetBlock chain
+ * (trajectory_module.py:54-60,104-122) — so that the following m4d_groupnorm_apply_cl needs no
+ * statistics pass.  partials_ws: T * ceil(H/16) * ceil(W/16) * 64 floats of scratch; stats:
+ * T * M4D_GN_SLICES * 64 floats (sum, sum of squares per group and slice; deterministic). */
+#define M4D_GN_SLICES 8
+int m4d_conv3x3_gnstats_cl(const void* x, int T, int H, int W, int Cin, const void* w_packed, int Cout,
+                           const void* bias, void* out, const void* residual, float* partials_ws,
+                           float* stats, void* stream);
+
+/* The apply pass of m4d_groupnorm_swish_cl with statistics given as `slices` partial
+ * (sum, sum of squares) sets per frame: stats[f][slice][group][2]. */
+int m4d_groupnorm_apply_cl(const void* x, const void* weight, const void* bias, void* out,
+                           const float* stats, int slices, int F, int HW, int C, int groups, float eps,
+                           void* stream);
+
 /* GroupNorm(32, eps, affine) + x*sigmoid(x) on [F, HW, C] channels-last
  * (trajectory_module.py:54-60); stats_ws: 64*F floats of scratch. */
 int m4d_groupnorm_swish_cl(const void* x, const void* weight, const void* bias, void* out,

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "m4d_planar_to_cl": (c_int, [_P, _P, _L, _I, _I, _P, _P, _P]),
     "m4d_cl_to_planar": (c_int, [_P, _P, _L, _I, _I, _P, _P, _P]),
     "m4d_groupnorm_swish_cl": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "m4d_conv3x3_gnstats_cl": (c_int, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "m4d_groupnorm_apply_cl": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "m4d_softmax_rows": (c_int, [_P, _P, _I, _I, _L, _L, _F, _P]),
     "m4d_transpose_bf16": (c_int, [_P, _P, _I, _I, _L, _L, _P]),
     "m4d_im2col3x3_cl": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),

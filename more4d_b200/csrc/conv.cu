@@ -199,7 +199,7 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
                         int sh, int sw, int pt, int ph, int pw, int T_out, int H_out, int W_out,
                         void* out, int out_C, int t_mul, int t_off, int n_split,
                         const void* residual, int out_mode, int act, const void* skip,
-                        const void* norm_gamma, void* norm_out, int norm_silu, void* stream_) {
+                        const void* norm_gamma, void* norm_out, int norm_silu, float* gn_partials, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(x && w_packed && (out || norm_out), M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(T_in > 0 && H_in > 0 && W_in > 0 && T_out > 0 && H_out > 0 && W_out > 0, M4D_ERR_BAD_SHAPE);
@@ -239,6 +239,7 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
   p.norm_gamma = static_cast<const bf16*>(norm_gamma);
   p.norm_out = static_cast<bf16*>(norm_out);
   p.norm_silu = norm_silu;
+  p.gn_partials = gn_partials;
   p.vec_ok = (out_mode == 0 && out_C % 8 == 0 && n_split % 8 == 0 && (out == nullptr || aligned16(out)) &&
               (bias == nullptr || aligned16(bias)) && (residual == nullptr || aligned16(residual)))
                  ? 1 : 0;
@@ -252,7 +253,7 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
   if (use_halo &&
       conv_halo_eligible(Cin, kt, kh, kw, st, sh, sw, pt, ph, pw, T_in, H_in, W_in, T_out, H_out, W_out))
     return conv_halo_launch(x, T_in, H_in, W_in, w_packed, Cout_pad, p, stream);
-  M4D_REQUIRE(norm_out == nullptr, M4D_ERR_UNSUPPORTED);      // the fused norm lives in conv_halo.cu
+  M4D_REQUIRE(norm_out == nullptr && gn_partials == nullptr, M4D_ERR_UNSUPPORTED);   // fused norms live in conv_halo.cu
   M4D_REQUIRE(Cin % CV_KB == 0, M4D_ERR_UNSUPPORTED);         // per-tap kernel: 32-channel boxes
 
   CUtensorMap tmX, tmW;
@@ -313,7 +314,7 @@ extern "C" int m4d_conv_cl(const void* x, int T_in, int H_in, int W_in, int Cin,
                            void* stream_) {
   return conv_cl_impl(x, T_in, H_in, W_in, Cin, w_packed, Cout, Cout_pad, bias, kt, kh, kw, st, sh, sw, pt,
                       ph, pw, T_out, H_out, W_out, out, out_C, t_mul, t_off, n_split, residual, out_mode,
-                      act, skip, nullptr, nullptr, 0, stream_);
+                      act, skip, nullptr, nullptr, 0, nullptr, stream_);
 }
 
 extern "C" int m4d_conv3x3_rmsnorm_cl(const void* x, int T, int H, int W, int Cin, const void* w_packed,
@@ -322,5 +323,49 @@ extern "C" int m4d_conv3x3_rmsnorm_cl(const void* x, int T, int H, int W, int Ci
   M4D_REQUIRE(gamma && norm_out && (kt == 1 || kt == 3), M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(Cout == 96 || Cout == 192, M4D_ERR_UNSUPPORTED);
   return conv_cl_impl(x, T, H, W, Cin, w_packed, Cout, Cout, bias, kt, 3, 3, 1, 1, 1, kt - 1, 1, 1, T, H, W,
-                      out, Cout, 1, 0, Cout, residual, 0, 0, nullptr, gamma, norm_out, do_silu, stream_);
+                      out, Cout, 1, 0, Cout, residual, 0, 0, nullptr, gamma, norm_out, do_silu, nullptr, stream_);
+}
+
+namespace m4d {
+// stats[f][slice][64] = sum over the slice's tiles of partials[f * tiles + tile][64], in tile order
+// (deterministic: no atomics anywhere on the fused GroupNorm-statistics path)
+__global__ void __launch_bounds__(256)
+gn_reduce_kernel(const float* __restrict__ partials, float* __restrict__ stats, int tiles) {
+  __shared__ float sh[4][64];
+  const int f = blockIdx.y, slice = blockIdx.x, slices = gridDim.x;
+  const int per = (tiles + slices - 1) / slices;
+  const int t0 = slice * per, t1 = min(tiles, t0 + per);
+  const int lane64 = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const float* base = partials + static_cast<long long>(f) * tiles * 64 + lane64;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int t = t0 + sub;
+  for (; t + 12 < t1; t += 16) {                       // four loads in flight
+    a0 += base[static_cast<long long>(t) * 64];
+    a1 += base[static_cast<long long>(t + 4) * 64];
+    a2 += base[static_cast<long long>(t + 8) * 64];
+    a3 += base[static_cast<long long>(t + 12) * 64];
+  }
+  for (; t < t1; t += 4) a0 += base[static_cast<long long>(t) * 64];
+  sh[sub][lane64] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (threadIdx.x < 64)
+    stats[(static_cast<long long>(f) * slices + slice) * 64 + threadIdx.x] =
+        (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+}
+}  // namespace m4d
+
+extern "C" int m4d_conv3x3_gnstats_cl(const void* x, int T, int H, int W, int Cin, const void* w_packed, int Cout,
+                                      const void* bias, void* out, const void* residual, float* partials_ws,
+                                      float* stats, void* stream_) {
+  using namespace m4d;
+  M4D_REQUIRE(out && partials_ws && stats, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(Cout == 128, M4D_ERR_UNSUPPORTED);              // 32 groups x 4 channels, one N tile
+  int rc = conv_cl_impl(x, T, H, W, Cin, w_packed, Cout, Cout, bias, 1, 3, 3, 1, 1, 1, 0, 1, 1, T, H, W, out, Cout,
+                        1, 0, Cout, residual, 0, 0, nullptr, nullptr, nullptr, 0, partials_ws, stream_);
+  if (rc != M4D_OK) return rc;
+  const int tiles = ((H + 15) / 16) * ((W + 15) / 16);
+  M4D_REQUIRE(T <= 65535, M4D_ERR_BAD_SHAPE);
+  gn_reduce_kernel<<<dim3(M4D_GN_SLICES, T), 256, 0, static_cast<cudaStream_t>(stream_)>>>(partials_ws, stats, tiles);
+  M4D_CHECK_LAUNCH("gn_reduce_kernel");
+  return M4D_OK;
 }

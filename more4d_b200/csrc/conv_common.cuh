@@ -37,6 +37,9 @@ struct ConvParams {
   bf16* norm_out;
   int norm_silu;
   int vec_ok;               // NHWC rows, bias and residual allow 16-byte vector access per 32 channels
+  // fused GroupNorm statistics (conv_halo.cu, NT == Cout == 128, 32 groups of 4 channels): per
+  // spatial tile the sums and sums of squares of the bf16 outputs, [tile][group][2] floats
+  float* gn_partials;
 };
 
 

@@ -140,17 +140,56 @@ __device__ __forceinline__ void rmsnorm_pass2(const ConvParams& p, long long pix
   }
 }
 
+// GroupNorm(32 groups x 4 channels) statistics of one tile (trajectory_module.py:54-60): every
+// thread holds its pixel's 128 bf16 outputs; per group (sum, sum of squares) -> 64 values, summed
+// over the warp's 32 pixels by recursive halving (62 shuffles: lane L ends with group L's pair),
+// over the CTA's 8 epilogue warps through shared memory, and stored as this tile's partial.  The
+// order of every addition is fixed, so the statistics are reproducible run to run.
+__device__ __forceinline__ void gn_tile_stats(const uint32_t* yp, bool pix_ok, float* gsm /*[8][64]*/,
+                                              float* partial /*[64]*/, int ewarp, int lane) {
+  float v[64];
+#pragma unroll
+  for (int g = 0; g < 32; ++g) {
+    const float a = bf16_lo(yp[2 * g]), b = bf16_hi(yp[2 * g]), c = bf16_lo(yp[2 * g + 1]), d = bf16_hi(yp[2 * g + 1]);
+    v[2 * g] = pix_ok ? (a + b) + (c + d) : 0.f;
+    v[2 * g + 1] = pix_ok ? (a * a + b * b) + (c * c + d * d) : 0.f;
+  }
+#pragma unroll
+  for (int half = 32, m = 16; m >= 1; half >>= 1, m >>= 1) {
+    const bool upper = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  *reinterpret_cast<float2*>(gsm + ewarp * 64 + 2 * lane) = make_float2(v[0], v[1]);
+  named_bar_sync(1, 256);                              // the 8 epilogue warps
+  if (ewarp < 2) {
+    const int j = ewarp * 32 + lane;
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += gsm[w8 * 64 + j];
+    partial[j] = t;
+  }
+}
+
 // One tile of the vector epilogue: pass 1, release the accumulators, pass 2 (NORM: the fused
 // RMS_norm; otherwise just the stores of the full NTC-channel row).
 template <int NTC, bool NORM, typename Release>
 __device__ __forceinline__ void epilogue_vec(const ConvParams& p, uint32_t t_row, long long pix_off, int n0,
                                              bool pix_ok, bool has_res, uint4* rnext, Release& release, int acc,
-                                             int lane) {
+                                             int lane, float* gsm = nullptr, float* partial = nullptr,
+                                             int ewarp = 0) {
   uint32_t yp[NTC / 2];
   const float ss = drain_pass1<NTC, NORM>(p, t_row, pix_off, n0, pix_ok, has_res, rnext, yp);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) release(acc);
+  if (NTC == 128 && !NORM) {
+    if (partial != nullptr) gn_tile_stats(yp, pix_ok, gsm, partial, ewarp, lane);   // warp-uniform branch
+  }
   if (!pix_ok) return;
   if (NORM) {
     rmsnorm_pass2<NTC>(p, pix_off, yp, ss);
@@ -239,6 +278,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* tfull = b_empty + CH_MAX_B;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* gsm = reinterpret_cast<float*>(tmem_slot + 4);    // [2][8][64] floats, GroupNorm-statistics mode only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -455,7 +495,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                  (p.NT == 96 || p.NT == 128 || p.NT == 192)) {    // warp-uniform
         // full-width tiles of the plain convs (96 / 128 / 192 / 2 x 192 channels): same drain-release-store
         if (p.NT == 96) epilogue_vec<96, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
-        else if (p.NT == 128) epilogue_vec<128, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
+        else if (p.NT == 128) {
+          // spatial tile index = (t, h_blk, w_blk); only written for tiles that exist
+          float* partial = (p.gn_partials != nullptr && t < p.T_out)
+                               ? p.gn_partials + ((static_cast<long long>(t) * tiles_h + h_blk) * tiles_w + w_blk) * 64
+                               : nullptr;
+          if (p.gn_partials != nullptr && partial == nullptr) partial = gsm + 2 * 512;   // odd tail's peer: scratch
+          epilogue_vec<128, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane,
+                                   gsm + (it & 1) * 512, partial, warp - 4);
+        }
         else epilogue_vec<192, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
         continue;
       } else {
@@ -512,6 +560,9 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   p.acc_bufs = (4 * p.acc_stride <= 512) ? 2 : 1;
   p.desc_mode = 0;
   M4D_REQUIRE(p.out_mode == 1 || p.n_split >= p.Cout, M4D_ERR_UNSUPPORTED);
+  if (p.gn_partials != nullptr)
+    M4D_REQUIRE(p.norm_out == nullptr && p.vec_ok && p.out_mode == 0 && NT == 128 && p.Cout == 128 && p.n_tiles == 1,
+                M4D_ERR_UNSUPPORTED);
   if (p.norm_out != nullptr) {
     M4D_REQUIRE(p.vec_ok, M4D_ERR_ALIGN);
     M4D_REQUIRE(p.norm_gamma != nullptr && p.out_mode == 0 && p.n_tiles == 1 && NT == p.Cout &&
@@ -532,7 +583,7 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   if (g_dev_flags & 0x4000) pair = false;
 #endif
   const int b_bytes = (pair ? NT / 2 : NT) * 128;       // per CTA and weight stage
-  const int fixed = 1024 + 512;                         // alignment slack + barriers
+  const int fixed = 1024 + 512 + (p.gn_partials ? 5 * 1024 : 0);   // alignment slack + barriers (+ statistics staging)
   // weight ring: all stages of a block when that leaves room for >= 2 halo stages, else 3
   int bst = (CH_SMEM_MAX - fixed - 9 * b_bytes >= 2 * CH_A_STRIDE) ? 9 : 3;
   if (tpb == 2) bst = 5;

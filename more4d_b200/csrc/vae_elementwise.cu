@@ -195,7 +195,7 @@ groupnorm_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, in
 // time.)
 constexpr int GN_VPT = 8;
 __global__ void __launch_bounds__(256)
-groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, int slices,
                        const bf16* __restrict__ w, const bf16* __restrict__ b, bf16* __restrict__ out,
                        int HW, int C, int cpg, float eps) {
   extern __shared__ float ab[];                   // A[C] | B[C]
@@ -203,8 +203,13 @@ groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ sta
   const float n = static_cast<float>(HW) * cpg;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float mean = stats[f * 64 + g * 2] / n;
-    const float var = fmaxf(stats[f * 64 + g * 2 + 1] / n - mean * mean, 0.f);
+    float s1 = 0.f, s2 = 0.f;
+    for (int sl = 0; sl < slices; ++sl) {              // fixed order: reproducible
+      s1 += stats[(f * slices + sl) * 64 + g * 2];
+      s2 += stats[(f * slices + sl) * 64 + g * 2 + 1];
+    }
+    const float mean = s1 / n;
+    const float var = fmaxf(s2 / n - mean * mean, 0.f);
     const float a = rsqrtf(var + eps) * __bfloat162float(w[c]);
     ab[c] = a;
     ab[C + c] = __bfloat162float(b[c]) - mean * a;
@@ -268,6 +273,59 @@ softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int N, lo
   const float inv = 1.f / sum;
   for (int i = threadIdx.x; i < N; i += blockDim.x)
     pr[i] = __float2bfloat16_rn(__expf((sr[i] - mx) * scale) * inv);
+}
+
+// Same, the row held in registers: ONE 16-byte-vector read of the logits, one exponential per
+// element, 8-byte stores (the three-pass kernel above re-read the row from L1/L2 three times with
+// 4-byte loads and evaluated every exponential twice: 0.27 of the HBM roofline at [14400, 14400],
+// profiles/rows_r02.md).  N % 4 == 0, N <= 1024 * SR_VPT, rows 16-byte (fp32) / 8-byte (bf16) aligned.
+constexpr int SR_VPT = 16;
+__global__ void __launch_bounds__(256)
+softmax_rows_reg_kernel(const float* __restrict__ s, bf16* __restrict__ p, int N, long long lds,
+                        long long ldp, float scale) {
+  __shared__ float red[2][8];
+  const float4* sr = reinterpret_cast<const float4*>(s + static_cast<long long>(blockIdx.x) * lds);
+  uint2* pr = reinterpret_cast<uint2*>(p + static_cast<long long>(blockIdx.x) * ldp);
+  const int nv = N >> 2;
+  float4 v[SR_VPT];
+#pragma unroll
+  for (int k = 0; k < SR_VPT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    v[k] = i < nv ? __ldcs(sr + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < SR_VPT; ++k) mx = fmaxf(fmaxf(mx, fmaxf(v[k].x, v[k].y)), fmaxf(v[k].z, v[k].w));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0][0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[0][i]);
+  const float c = scale * 1.4426950408889634f;
+  const float mc = mx * c;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < SR_VPT; ++k) {
+    v[k].x = fast_exp2(fmaf(v[k].x, c, -mc));
+    v[k].y = fast_exp2(fmaf(v[k].y, c, -mc));
+    v[k].z = fast_exp2(fmaf(v[k].z, c, -mc));
+    v[k].w = fast_exp2(fmaf(v[k].w, c, -mc));
+    sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  sum = wsum(sum);
+  if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[1][i];
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < SR_VPT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nv) __stcs(pr + i, make_uint2(pack_bf16(v[k].x * inv, v[k].y * inv), pack_bf16(v[k].z * inv, v[k].w * inv)));
+  }
 }
 
 // out[c, r] = in[r, c]  (bf16), 32x32 smem tiles; in row stride ld_in, out row stride ld_out
@@ -369,8 +427,27 @@ extern "C" int m4d_groupnorm_swish_cl(const void* x, const void* weight, const v
   const int cap = (8 * sm_count() + F - 1) / F > 1 ? (8 * sm_count() + F - 1) / F : 1;   // ~8 blocks per SM
   if (gx > cap) gx = cap;
   groupnorm_swish_kernel<<<dim3(gx, F), 256, 2 * C * sizeof(float), stream>>>(
-      static_cast<const bf16*>(x), stats_ws, static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),
+      static_cast<const bf16*>(x), stats_ws, 1, static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),
       static_cast<bf16*>(out), HW, C, cpg, eps);
+  M4D_CHECK_LAUNCH("groupnorm_swish_kernel");
+  return M4D_OK;
+}
+
+extern "C" int m4d_groupnorm_apply_cl(const void* x, const void* weight, const void* bias, void* out,
+                                      const float* stats, int slices, int F, int HW, int C, int groups, float eps,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  M4D_REQUIRE(x && weight && bias && out && stats && F > 0 && HW > 0 && slices > 0, M4D_ERR_BAD_SHAPE);
+  M4D_REQUIRE(groups == 32 && C % (groups * 4) == 0 && C <= 1024, M4D_ERR_UNSUPPORTED);
+  M4D_REQUIRE(aligned16(x) && aligned16(out) && aligned16(weight) && aligned16(bias), M4D_ERR_ALIGN);
+  M4D_REQUIRE(F <= 65535 && static_cast<long long>(HW) * (C / 8) < (1ll << 31), M4D_ERR_BAD_SHAPE);
+  const int per_frame = HW * (C / 8);
+  int gx = (per_frame + 256 * GN_VPT - 1) / (256 * GN_VPT);
+  const int cap = (8 * sm_count() + F - 1) / F > 1 ? (8 * sm_count() + F - 1) / F : 1;
+  if (gx > cap) gx = cap;
+  groupnorm_swish_kernel<<<dim3(gx, F), 256, 2 * C * sizeof(float), stream>>>(
+      static_cast<const bf16*>(x), stats, slices, static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),
+      static_cast<bf16*>(out), HW, C, C / groups, eps);
   M4D_CHECK_LAUNCH("groupnorm_swish_kernel");
   return M4D_OK;
 }
@@ -379,6 +456,12 @@ extern "C" int m4d_softmax_rows(const float* s, void* p, int rows, int N, long l
                                 float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(s && p && rows > 0 && N > 0 && lds >= N && ldp >= N, M4D_ERR_BAD_SHAPE);
+  if (N % 4 == 0 && N <= 1024 * SR_VPT && lds % 4 == 0 && ldp % 4 == 0 && aligned16(s) &&
+      (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+    softmax_rows_reg_kernel<<<rows, 256, 0, stream>>>(s, static_cast<bf16*>(p), N, lds, ldp, scale);
+    M4D_CHECK_LAUNCH("softmax_rows_reg_kernel");
+    return M4D_OK;
+  }
   softmax_rows_kernel<<<rows, 256, 0, stream>>>(s, static_cast<bf16*>(p), N, lds, ldp, scale);
   M4D_CHECK_LAUNCH("softmax_rows_kernel");
   return M4D_OK;

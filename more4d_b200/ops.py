@@ -559,13 +559,48 @@ def cl_to_planar(x: Tensor, n_affine: int = 0, sub: Optional[Tensor] = None,
     return out
 
 
+GN_SLICES = 8                          # M4D_GN_SLICES of include/more4d_b200.h
+
+
+def conv3x3_gnstats_cl(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int,
+                       residual: Optional[Tensor] = None):
+    """3x3 Conv2d per frame ([T, H, W, Cin] -> [T, H, W, 128]) whose epilogue also leaves the
+    GroupNorm(32) statistics of its output (`stats` for groupnorm_swish_cl): returns (out, stats)."""
+    _lib.require_device()
+    _req(x, BF16, "x")
+    if not x.is_contiguous():
+        raise ValueError("more4d_b200.conv3x3_gnstats_cl: x must be contiguous [T, H, W, C]")
+    T, H, W, Cin = x.shape
+    if w_packed.shape != (cout, 9 * Cin):
+        raise ValueError("more4d_b200.conv3x3_gnstats_cl: packed weight does not match (cout, 9 * Cin)")
+    out = torch.empty(T, H, W, cout, device=x.device, dtype=BF16)
+    tiles = ((H + 15) // 16) * ((W + 15) // 16)
+    ws = torch.empty(T * tiles * 64, device=x.device, dtype=torch.float32)
+    stats = torch.empty(T * GN_SLICES * 64, device=x.device, dtype=torch.float32)
+    _Stats.launches += 1                                   # conv + the partial-sum reduction
+    rc = _lib.lib().m4d_conv3x3_gnstats_cl(x.data_ptr(), T, H, W, Cin, w_packed.data_ptr(), cout, _ptr(bias),
+                                           out.data_ptr(), _ptr(residual), ws.data_ptr(), stats.data_ptr(),
+                                           _stream())
+    _lib.check(rc, "m4d_conv3x3_gnstats_cl")
+    return out, stats
+
+
 def groupnorm_swish_cl(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-6, groups: int = 32,
-                       inplace: bool = False) -> Tensor:
-    """GroupNorm + swish on [F, H, W, C] with per-frame statistics."""
+                       inplace: bool = False, stats: Optional[Tensor] = None) -> Tensor:
+    """GroupNorm + swish on [F, H, W, C] with per-frame statistics; `stats` (from
+    conv3x3_gnstats_cl, the producer of x) skips the statistics pass."""
     _lib.require_device()
     _req(x, BF16, "x")
     F_, H, W, C = x.shape
     out = x if inplace else torch.empty_like(x)
+    if stats is not None:
+        _req(stats, torch.float32, "stats")
+        if stats.numel() != F_ * GN_SLICES * 64:
+            raise ValueError("more4d_b200.groupnorm_swish_cl: stats do not belong to this tensor")
+        rc = _lib.lib().m4d_groupnorm_apply_cl(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                               stats.data_ptr(), GN_SLICES, F_, H * W, C, groups, eps, _stream())
+        _lib.check(rc, "m4d_groupnorm_apply_cl")
+        return out
     ws = torch.empty(64 * F_, device=x.device, dtype=torch.float32)
     _Stats.launches += 1                                   # stats + apply = two kernels
     rc = _lib.lib().m4d_groupnorm_swish_cl(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),

@@ -386,13 +386,22 @@ class _Adaptor(nn.Module):
         return ops.conv_cl(x, self._packed.get(name, w, mult), self._p(name + ".bias"), cout, (1, 3, 3),
                            pad=(0, 1, 1), **kw)
 
-    def _resnet(self, x: Tensor, p: str) -> Tensor:
-        """ResnetBlock.forward, temb = None, in == out channels (traj:104-122)."""
-        g = ops.groupnorm_swish_cl(x, self._p(p + ".norm1.weight"), self._p(p + ".norm1.bias"))
-        c1 = self._conv(g, p + ".conv1", self.ch)
+    def _conv_stats(self, x, name, residual=None):
+        """A 128-channel conv whose output feeds a Normalize: the GroupNorm statistics come out of
+        the conv's epilogue (ops.conv3x3_gnstats_cl).  Returns (out, stats)."""
+        w = self._p(name + ".weight")
+        mult = 16 if x.shape[-1] % 32 else 32
+        return ops.conv3x3_gnstats_cl(x, self._packed.get(name, w, mult), self._p(name + ".bias"), self.ch,
+                                      residual=residual)
+
+    def _resnet(self, x: Tensor, x_stats: Tensor, p: str):
+        """ResnetBlock.forward, temb = None, in == out channels (traj:104-122).  Takes and returns
+        (tensor, GroupNorm statistics of that tensor)."""
+        g = ops.groupnorm_swish_cl(x, self._p(p + ".norm1.weight"), self._p(p + ".norm1.bias"), stats=x_stats)
+        c1, s1 = self._conv_stats(g, p + ".conv1")
         del g
-        ops.groupnorm_swish_cl(c1, self._p(p + ".norm2.weight"), self._p(p + ".norm2.bias"), inplace=True)
-        return self._conv(c1, p + ".conv2", self.ch, residual=x)
+        ops.groupnorm_swish_cl(c1, self._p(p + ".norm2.weight"), self._p(p + ".norm2.bias"), inplace=True, stats=s1)
+        return self._conv_stats(c1, p + ".conv2", residual=x)
 
     def _forward_one(self, x: Tensor) -> Tensor:
         raise NotImplementedError
@@ -409,9 +418,9 @@ class VAEEncoderadaptor(_Adaptor):
     kind = "encoder"
 
     def _forward_one(self, x: Tensor) -> Tensor:          # x [3, F, H, W]
-        h = self._conv(ops.planar_to_cl(x, 16), "conv_in", self.ch)
-        h = self._resnet(h, "down.0.block.0")
-        ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True)
+        h, st = self._conv_stats(ops.planar_to_cl(x, 16), "conv_in")
+        h, st = self._resnet(h, st, "down.0.block.0")
+        ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True, stats=st)
         out = torch.empty_like(x)
         self._conv(h, "conv_out", 3, planar_out=out, act=2, skip=x)      # sigmoid(h + x), traj:194
         return out
@@ -422,10 +431,10 @@ class VAEDecoderadaptor(_Adaptor):
     kind = "decoder"
 
     def _forward_one(self, z: Tensor) -> Tensor:
-        h = self._conv(ops.planar_to_cl(z, 16), "conv_in", self.ch)
-        h = self._resnet(h, "up.0.block.0")
-        h = self._resnet(h, "up.0.block.1")
-        ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True)
+        h, st = self._conv_stats(ops.planar_to_cl(z, 16), "conv_in")
+        h, st = self._resnet(h, st, "up.0.block.0")
+        h, st = self._resnet(h, st, "up.0.block.1")
+        ops.groupnorm_swish_cl(h, self._p("norm_out.weight"), self._p("norm_out.bias"), inplace=True, stats=st)
         out = torch.empty_like(z)
         self._conv(h, "conv_out", 3, planar_out=out, act=0)
         return out

@@ -208,6 +208,13 @@ def test_row_kernels(ops):
     s = _rand((37, 24), 23, 3.0, torch.float32)
     p = ops.softmax_rows(s.cuda(), 0.25)
     assert rel_err(p.float().cpu(), torch.softmax(s * 0.25, -1)) < 3e-3
+    for n, tail in ((2052, 0), (14400, 0), (330, 8), (27, 0)):     # register-resident / 3-pass kernel, strided rows
+        s = _rand((9, n + tail), 28, 3.0, torch.float32)
+        s[3, 5] = 40.0                                              # one dominant logit
+        p = ops.softmax_rows(s.cuda()[:, :n], 0.125)
+        ref = torch.softmax(s[:, :n] * 0.125, -1)
+        assert rel_err(p.float().cpu(), ref) < 3e-3
+        assert (p.float().sum(-1).cpu() - 1).abs().max() < 1e-2
     m = _rand((45, 70), 24)
     assert torch.equal(ops.transpose_bf16(m.cuda()).cpu(), m.t().contiguous())
     xa = _rand((1, 128, 3, 6, 10), 25, 2.0)
@@ -215,6 +222,34 @@ def test_row_kernels(ops):
     refg = V._group_norm_swish(xa[0].permute(1, 0, 2, 3).float(), w, b, AR)            # [F, C, H, W]
     yg = ops.groupnorm_swish_cl(_cl(xa), w.cuda(), b.cuda())
     assert rel_err(yg.float().cpu().permute(0, 3, 1, 2), refg) < 4e-3
+
+
+@pytest.mark.parametrize("T,H,W,cin,res", [(3, 33, 47, 128, True), (2, 16, 32, 16, False), (1, 50, 20, 128, False)])
+def test_conv_with_fused_groupnorm_statistics(ops, T, H, W, cin, res):
+    """m4d_conv3x3_gnstats_cl: same conv output as m4d_conv_cl, and the statistics its epilogue
+    leaves reproduce groupnorm_swish_cl's own statistics pass (trajectory_module.py:54-60);
+    odd tile counts exercise the CTA pair's idle half, cin 16 the thin-input kernel."""
+    x = _rand((1, cin, T, H, W), 71, 1.5)
+    w = _rand((128, cin, 3, 3), 72, 0.05)
+    b = _rand((128,), 73, 0.2)
+    r = _rand((1, 128, T, H, W), 74, 1.0) if res else None
+    gw, gb = _rand((128,), 75, 0.1) + 1, _rand((128,), 76, 0.1)
+    xc = _cl(x)
+    wp = ops.pack_conv_weight(w.cuda(), 16 if cin % 32 else 32)
+    rc = _cl(r) if res else None
+    ref = ops.conv_cl(xc, wp, b.cuda(), 128, (1, 3, 3), pad=(0, 1, 1), residual=rc)
+    out, stats = ops.conv3x3_gnstats_cl(xc, wp, b.cuda(), 128, residual=rc)
+    assert torch.equal(out, ref)
+    g_ref = ops.groupnorm_swish_cl(ref, gw.cuda(), gb.cuda())
+    g = ops.groupnorm_swish_cl(out, gw.cuda(), gb.cuda(), stats=stats)
+    assert rel_err(g.float().cpu(), g_ref.float().cpu()) < 2e-3
+    # the statistics themselves: per frame and group, sum and sum of squares of the bf16 output
+    st = stats.view(T, ops.GN_SLICES, 32, 2).sum(1).cpu()
+    o = out.float().cpu().view(T, H * W, 32, 4)
+    assert torch.allclose(st[..., 0], o.sum((1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[..., 1], (o * o).sum((1, 3)), rtol=1e-4, atol=1e-2)
+    out2, stats2 = ops.conv3x3_gnstats_cl(xc, wp, b.cuda(), 128, residual=rc)
+    assert torch.equal(stats, stats2)                                  # no atomics: reproducible
 
 
 def _vae():

@@ -15,6 +15,7 @@ class _Recorder:
         self.calls = collections.Counter()
         self.fused = []          # (cin, cout, want_raw, has_residual)
         self.norm_channels = []
+        self.stats_of = {}
 
     def t(self, *shape):
         return torch.empty(*shape, device="meta", dtype=torch.bfloat16)
@@ -58,6 +59,21 @@ class _Recorder:
         self.fused.append((Cin, cout, want_raw, residual is not None))
         return (self.t(T, H, W, cout) if want_raw else None), self.t(T, H, W, cout)
 
+    def conv3x3_gnstats_cl(self, x, w_packed, bias, cout, residual=None):
+        self.calls["conv3x3_gnstats_cl"] += 1
+        T, H, W, Cin = x.shape
+        assert cout == 128 and w_packed.shape == (cout, 9 * Cin)
+        out = self.t(T, H, W, cout)
+        stats = torch.empty(T * real_ops.GN_SLICES * 64, device="meta")
+        self.stats_of[id(stats)] = out
+        return out, stats
+
+    def groupnorm_swish_cl(self, x, weight, bias, eps=1e-6, groups=32, inplace=False, stats=None):
+        self.calls["groupnorm_swish_cl"] += 1
+        # the statistics handed over must be the ones of THIS tensor (left by its producing conv)
+        assert stats is not None and self.stats_of[id(stats)] is x
+        return x if inplace else self.t(*x.shape)
+
     def rmsnorm_silu_cl(self, x, gamma, silu=True, inplace=False):
         self.calls["rmsnorm_silu_cl"] += 1
         self.norm_channels.append(x.shape[-1])
@@ -72,13 +88,13 @@ class _Recorder:
         self.calls["linear"] += 1
         return out if out is not None else self.t(*x.shape[:-1], weight.shape[0])
 
-    def softmax_rows(self, s, scale):
+    def softmax_rows(self, s, scale, out=None):
         self.calls["softmax_rows"] += 1
-        return self.t(*s.shape)
+        return out if out is not None else self.t(*s.shape)
 
-    def transpose_bf16(self, m):
+    def transpose_bf16(self, m, out=None):
         self.calls["transpose_bf16"] += 1
-        return self.t(m.shape[1], m.shape[0])
+        return out if out is not None else self.t(m.shape[1], m.shape[0])
 
     FUSED_NORM_CHANNELS = real_ops.FUSED_NORM_CHANNELS
     EPI_F32_RAW, EPI_ADD_BF16 = real_ops.EPI_F32_RAW, real_ops.EPI_ADD_BF16
@@ -128,3 +144,15 @@ def test_decoder_plan(rec):
     assert any(cin == 192 and cout == 96 for cin, cout, _, _ in rec.fused)
     assert 96 not in rec.norm_channels and 192 not in rec.norm_channels
     assert rec.calls["upsample2x_cl"] == 3
+
+
+@pytest.mark.parametrize("cls,gn,convs", [(vae_mod.VAEEncoderadaptor, 3, 3), (vae_mod.VAEDecoderadaptor, 5, 5)])
+def test_adaptor_plan_every_groupnorm_gets_its_statistics_from_the_producing_conv(rec, cls, gn, convs):
+    """trajectory_module.py:104-122,125-279: conv_in and every ResnetBlock conv feed a Normalize; the
+    host hands each GroupNorm the statistics its producer's epilogue left (no statistics pass)."""
+    a = cls(device="meta")
+    x = torch.empty(3, 5, 32, 48, device="meta", dtype=torch.bfloat16)
+    out = a._forward_one(x)
+    assert tuple(out.shape) == (3, 5, 32, 48)
+    assert rec.calls["groupnorm_swish_cl"] == gn and rec.calls["conv3x3_gnstats_cl"] == convs
+    assert rec.calls["conv_cl"] == 1                                   # conv_out (planar 3-channel output)
