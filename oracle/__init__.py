@@ -16,7 +16,15 @@ Contents
 ``vae_oracle``  torch-fp32 restatement of the causal Wan VAE + trajectory adaptors.
 ``project_oracle``  numpy-float32 restatement of the z-buffer point projection
                 (``render_with_project``); reproduces the real function exactly on the goldens.
+``gs_oracle``   numpy restatement of the 3D-Gaussian-splatting forward rasteriser behind
+                ``gs_render`` (third-party ``diff_gaussian_rasterization`` is absent from the
+                reference tree: PARITY UNPINNED, see its header).
 ``cpu_baseline``  bounded-sample timing of the DiT oracle for ``bench.py``.
+
+``ref_import`` also carries the stand-ins the goldens need to run the REAL modules: an Euler flow
+scheduler and pipeline stubs for ``WanFunControlPipeline.__call__`` (``load_pipeline``), and a
+deterministic stub OmniMAE trunk (``load_with_stub_omnimae``) feeding the real ``feature_adapter``
+/ resize / repeat front end.  ``dit_oracle.mpm_front_end`` restates that front end.
 
 Parity pinning: the reference ships NO tests, golden vectors or fixtures,
 so parity is "unpinned by the reference's own tests".  The restatement is instead pinned
