@@ -75,7 +75,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in self.f:
             c = [v.strip() for v in line.split(",")]
             if len(c) < 9:
@@ -84,6 +84,10 @@ class ClockSampler:
                 sm.append(float(c[1])); mx.append(float(c[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(c[3]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -92,7 +96,7 @@ class ClockSampler:
         busy = sorted(sm)[len(sm) // 4:] if sm else []
         return {"sm_mhz": statistics.median(busy) if busy else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": statistics.median(pw) if pw else None}
 
 
 def cpu_reference_arm(args, cfg, L, grid, rank, repeats=1, skip=0):
@@ -178,7 +182,29 @@ def sequence_parallel_legs(args, cfg, model, den, dev, rank, world, frames, heig
     return rec
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: keep the real stdout for it and point fd 1 at stderr, so
+    that banners printed by C libraries (NCCL's version line under torchrun) cannot land in front of it."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -239,7 +265,7 @@ def main():
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -343,9 +369,24 @@ def main():
     cls_ms["other"] = cls_ms["step"] - sum(v for k, v in cls_ms.items() if k != "step")
     keys = sorted(cls_ms)
     cm = torch.tensor([cls_ms[k] for k in keys], device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's figures (identical work on every rank under weak scaling): the spread between
+        # chips is what separates the N-GPU step time (max over ranks) from the 1-GPU one
+        mine = torch.tensor([cls_ms[k] for k in keys] + [ev0.elapsed_time(ev1) / args.steps,
+                                                         float(clocks.get("sm_mhz") or 0.0),
+                                                         float(clocks.get("power_w") or 0.0)], device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu()
+        per_rank = {k: [round(float(v), 1) for v in allr[:, i]] for i, k in enumerate(keys)}
+        per_rank["timed_ms_per_step"] = [round(float(v), 1) for v in allr[:, len(keys)]]
+        per_rank["sm_mhz"] = [float(v) for v in allr[:, len(keys) + 1]]
+        per_rank["power_w"] = [round(float(v)) for v in allr[:, len(keys) + 2]]
         dist.all_reduce(cm, op=dist.ReduceOp.MAX)
     kernel_class_ms = {k: float(v) for k, v in zip(keys, cm.tolist())}
+    if per_rank is not None:
+        kernel_class_ms["per_rank"] = per_rank
     kernel_class_ms["gemm_tflops"] = sum(w for _, _, w in prof["gemm"]) / (cls_ms["gemm"] / 1e3) / 1e12 if cls_ms["gemm"] else None
     kernel_class_ms["note"] = ("one step with per-launch CUDA events on every block kernel (max over ranks per class); "
                                "`other` = embeddings, head, CFG/Euler, host gaps")
@@ -408,7 +449,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cb, "kernel_class_ms": kernel_class_ms,
             "vae_roundtrip": vae_record, "sp": sp_record,
             "sp_bit_exact": None if sp_record is None else sp_record.get("bit_exact")}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
