@@ -290,6 +290,7 @@ rmsnorm_rope_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
 // four (cos, sin) pairs once per row instead of two table loads per pair and head.
 constexpr int RW_MAXV = 10;          // 16-byte vectors per lane: C <= 2 warps * 32 lanes * 8 * 10 = 5120
 constexpr int RW_WARPS = 8;          // per CTA: 4 rows x 2 warps
+template <bool NORM>
 __global__ void __launch_bounds__(RW_WARPS * 32, 2)
 rmsnorm_rope_warp_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
                          const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
@@ -325,10 +326,10 @@ rmsnorm_rope_warp_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
     }
   }
   float rstd = 1.f;
-  if (weight != nullptr) {
+  if (NORM) {
     ss = warp_sum(ss);
     if (lane == 0) part[warp] = ss;
-    __syncthreads();
+    named_bar_sync(1 + (warp >> 1), 64);           // the row's two warps only; other rows do not wait
     rstd = bf16_round(rsqrtf((part[warp & ~1] + part[warp | 1]) / C + eps));   // same order in both warps
   }
 
@@ -352,27 +353,22 @@ rmsnorm_rope_warp_kernel(bf16* __restrict__ x, const bf16* __restrict__ weight,
       }
     }
   }
-  // the norm weight (10 KB, L1/L2 resident) is fetched one vector ahead of its use
-  const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-  const int v0 = lane + wr * 32;
-  uint4 gw_next = (weight != nullptr && v0 < nvec) ? __ldg(reinterpret_cast<const uint4*>(weight + v0 * 8)) : ones;
+  const uint32_t rstd2 = pack_bf16(rstd, rstd);
+  // the norm weight (10 KB) stays L1 resident; 16 warps per SM cover its latency
 #pragma unroll
   for (int i = 0; i < RW_MAXV; ++i) {
     const int vi = lane + (2 * i + wr) * 32;
-    const uint4 gw = gw_next;
-    if (i + 1 < RW_MAXV && weight != nullptr && vi + 64 < nvec)
-      gw_next = __ldg(reinterpret_cast<const uint4*>(weight + (vi + 64) * 8));
     if (live && vi < nvec) {
+      uint4 gw = make_uint4(0, 0, 0, 0);
+      if (NORM) gw = __ldg(reinterpret_cast<const uint4*>(weight + vi * 8));
       const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
       const uint32_t g[4] = {gw.x, gw.y, gw.z, gw.w};
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float re = __uint_as_float(w[e] << 16), im = __uint_as_float(w[e] & 0xFFFF0000u);
-        if (weight != nullptr) {
-          re = bf16_round(bf16_round(re * rstd) * __uint_as_float(g[e] << 16));
-          im = bf16_round(bf16_round(im * rstd) * __uint_as_float(g[e] & 0xFFFF0000u));
-        }
+        // bf16(bf16(x * rstd) * w) with rstd already rounded to bf16 (t4d:378-394): two packed multiplies
+        const uint32_t xn = NORM ? mul_bf16x2(mul_bf16x2(w[e], rstd2), g[e]) : w[e];
+        float re = bf16_lo(xn), im = bf16_hi(xn);
         if (rope) {
           const float r2 = re * cs[e] - im * sn[e];
           const float i2 = re * sn[e] + im * cs[e];
@@ -698,7 +694,8 @@ extern "C" int m4d_rmsnorm_rope(void* x, long long row_stride, const void* weigh
   if (head_dim == 128 && C <= 2 * 32 * 8 * RW_MAXV && row_stride % 8 == 0 && aligned16(x) &&
       (weight == nullptr || aligned16(weight))) {
     const unsigned grid = static_cast<unsigned>((rows + RW_WARPS / 2 - 1) / (RW_WARPS / 2));
-    rmsnorm_rope_warp_kernel<<<grid, RW_WARPS * 32, 0, stream>>>(
+    auto kern = weight != nullptr ? rmsnorm_rope_warp_kernel<true> : rmsnorm_rope_warp_kernel<false>;
+    kern<<<grid, RW_WARPS * 32, 0, stream>>>(
         static_cast<bf16*>(x), static_cast<const bf16*>(weight), rope_cos, rope_sin, grid_fhw, rows, L, C, eps,
         row_stride);
     M4D_CHECK_LAUNCH("rmsnorm_rope_warp_kernel");
