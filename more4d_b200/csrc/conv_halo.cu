@@ -110,7 +110,6 @@ __device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row
       conv_packed<2>(rr[cur], p.bias ? p.bias + n0 + cc : nullptr, has_res ? rcur + 2 * hf : nullptr, y + hf * 8);
     }
     if (NORM) {
-      if (p.out != nullptr && pix_ok) store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, y);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a = bf16_lo(y[i]), b = bf16_hi(y[i]);
@@ -192,6 +191,11 @@ __device__ __forceinline__ void epilogue_vec(const ConvParams& p, uint32_t t_row
   }
   if (!pix_ok) return;
   if (NORM) {
+    if (p.out != nullptr) {                         // the raw output (x + h) some later shortcut consumes
+#pragma unroll
+      for (int c0 = 0; c0 < NTC; c0 += 32)
+        store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, yp + (c0 >> 1));
+    }
     rmsnorm_pass2<NTC>(p, pix_off, yp, ss);
   } else {
 #pragma unroll

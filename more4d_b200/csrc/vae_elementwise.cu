@@ -85,20 +85,28 @@ rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamm
 }
 
 // nearest-exact 2x spatial upsample (wan_vae.py:61-67,82-83) on [T, H, W, C] -> [T, 2H, 2W, C]
-__global__ void upsample2x_cl_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, int H,
-                                     int W, int C8) {
-  // one thread = one 16-byte vector of one OUTPUT pixel
-  const long long total = static_cast<long long>(T) * 2 * H * 2 * W * C8;
+__global__ void __launch_bounds__(256)
+upsample2x_cl_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, int H, int W, int C8) {
+  // one thread = one 16-byte vector of one INPUT pixel, read once (streaming) and written to its four
+  // output pixels; consecutive threads cover consecutive vectors, so every store instruction of a
+  // warp writes whole 512-byte runs of an output row.  (The first version ran one thread per OUTPUT
+  // vector: four times the index arithmetic and every input vector fetched four times: 0.60 of the
+  // HBM roofline, profiles/rows_r02.md.)
+  const long long total = static_cast<long long>(T) * H * W * C8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c = static_cast<int>(idx % C8);
   long long r = idx / C8;
-  const int wo = static_cast<int>(r % (2 * W)); r /= 2 * W;
-  const int ho = static_cast<int>(r % (2 * H));
-  const int t = static_cast<int>(r / (2 * H));
-  const uint4* src = reinterpret_cast<const uint4*>(x) +
-                     ((static_cast<long long>(t) * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c;
-  reinterpret_cast<uint4*>(out)[idx] = __ldg(src);
+  const int wi = static_cast<int>(r % W); r /= W;
+  const int hi = static_cast<int>(r % H);
+  const long long t = r / H;
+  const uint4 v = __ldcs(reinterpret_cast<const uint4*>(x) + idx);
+  uint4* o = reinterpret_cast<uint4*>(out) + ((t * 2 * H + 2 * hi) * (2 * W) + 2 * wi) * C8 + c;
+  const long long row = static_cast<long long>(2 * W) * C8;
+  __stcs(o, v);
+  __stcs(o + C8, v);
+  __stcs(o + row, v);
+  __stcs(o + row + C8, v);
 }
 
 // planar [C, T, H, W] -> channels-last [T*H*W, Cpad] (zero-padded channels) with the decoder's
@@ -219,6 +227,18 @@ groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ sta
   const int per_frame = HW * nvec;                // 16-byte vectors per frame
   const uint4* xf = reinterpret_cast<const uint4*>(x) + static_cast<long long>(f) * per_frame;
   uint4* of = reinterpret_cast<uint4*>(out) + static_cast<long long>(f) * per_frame;
+  // 256 % nvec == 0 (C in {128, 256, ...}): a thread always lands on the same 8 channels, so its
+  // (A, B) live in registers and the loop has no shared-memory loads and no index arithmetic
+  const bool fixed_c = (256 % nvec) == 0;
+  float Ar[8], Br[8];
+  if (fixed_c) {
+    const int c0 = (threadIdx.x % nvec) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      Ar[e] = ab[c0 + e];
+      Br[e] = ab[C + c0 + e];
+    }
+  }
   for (int i0 = blockIdx.x * (256 * GN_VPT) + threadIdx.x; i0 < per_frame; i0 += gridDim.x * (256 * GN_VPT)) {
     uint4 v[GN_VPT];
 #pragma unroll
@@ -228,16 +248,25 @@ groupnorm_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ sta
     for (int k = 0; k < GN_VPT; ++k) {
       const int i = i0 + k * 256;
       if (i >= per_frame) break;
-      const int c0 = (i % nvec) * 8;
       const uint32_t xs[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
       uint32_t o[4];
+      if (fixed_c) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 A = *reinterpret_cast<const float2*>(&ab[c0 + 2 * e]);
-        const float2 B = *reinterpret_cast<const float2*>(&ab[C + c0 + 2 * e]);
-        // y = bf16(x * A + B); swish = bf16(y * bf16(sigmoid(y)))   (x * torch.sigmoid(x) on bf16 tensors)
-        const uint32_t y = pack_bf16(fmaf(bf16_lo(xs[e]), A.x, B.x), fmaf(bf16_hi(xs[e]), A.y, B.y));
-        o[e] = mul_bf16x2(y, sigmoid_bf16x2(y));
+        for (int e = 0; e < 4; ++e) {
+          // y = bf16(x * A + B); swish = bf16(y * bf16(sigmoid(y)))   (x * torch.sigmoid(x) on bf16 tensors)
+          const uint32_t y = pack_bf16(fmaf(bf16_lo(xs[e]), Ar[2 * e], Br[2 * e]),
+                                       fmaf(bf16_hi(xs[e]), Ar[2 * e + 1], Br[2 * e + 1]));
+          o[e] = mul_bf16x2(y, sigmoid_bf16x2(y));
+        }
+      } else {
+        const int c0 = (i % nvec) * 8;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 A = *reinterpret_cast<const float2*>(&ab[c0 + 2 * e]);
+          const float2 B = *reinterpret_cast<const float2*>(&ab[C + c0 + 2 * e]);
+          const uint32_t y = pack_bf16(fmaf(bf16_lo(xs[e]), A.x, B.x), fmaf(bf16_hi(xs[e]), A.y, B.y));
+          o[e] = mul_bf16x2(y, sigmoid_bf16x2(y));
+        }
       }
       __stcs(of + i, make_uint4(o[0], o[1], o[2], o[3]));
     }
@@ -368,7 +397,7 @@ extern "C" int m4d_upsample2x_cl(const void* x, void* out, int T, int H, int W, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   M4D_REQUIRE(x && out && T > 0 && H > 0 && W > 0 && C > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(out), M4D_ERR_ALIGN);
-  const long long total = static_cast<long long>(T) * 4 * H * W * (C / 8);
+  const long long total = static_cast<long long>(T) * H * W * (C / 8);
   const long long blocks = (total + 255) / 256;
   M4D_REQUIRE(blocks < (1ll << 31), M4D_ERR_BAD_SHAPE);
   upsample2x_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
