@@ -243,6 +243,10 @@ static int conv_cl_impl(const void* x, int T_in, int H_in, int W_in, int Cin, co
   p.vec_ok = (out_mode == 0 && out_C % 8 == 0 && n_split % 8 == 0 && (out == nullptr || aligned16(out)) &&
               (bias == nullptr || aligned16(bias)) && (residual == nullptr || aligned16(residual)))
                  ? 1 : 0;
+  // 32-byte aligned pixel rows: the vector epilogues use 256-bit loads / stores
+  if (p.vec_ok && out_C % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 &&
+      (reinterpret_cast<uintptr_t>(residual) & 31) == 0 && n_split >= Cout)
+    p.vec_ok = 2;
 
   // 3x3 (x kt) stride-1 convolutions — almost all of the VAE's FLOPs — take the halo-staging
   // kernel (conv_halo.cu); development builds: flag 0x10000 forces the per-tap kernel below.

@@ -36,7 +36,8 @@ struct ConvParams {
   const bf16* norm_gamma;
   bf16* norm_out;
   int norm_silu;
-  int vec_ok;               // NHWC rows, bias and residual allow 16-byte vector access per 32 channels
+  int vec_ok;               // NHWC rows, bias and residual allow 16-byte vector access per 32 channels;
+                            // 2: rows (out, residual, norm_out) are also 32-byte aligned -> 256-bit accesses
   // fused GroupNorm statistics (conv_halo.cu, NT == Cout == 128, 32 groups of 4 channels): per
   // spatial tile the sums and sums of squares of the bf16 outputs, [tile][group][2] floats
   float* gn_partials;
@@ -57,6 +58,11 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
 __device__ __forceinline__ void load_res_chunk(const bf16* res, uint4* r4) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) r4[q] = reinterpret_cast<const uint4*>(res)[q];
+}
+// the same 64 bytes as two 256-bit loads (32-byte aligned rows: ConvParams::vec_ok == 2)
+__device__ __forceinline__ void load_res_chunk32(const bf16* res, uint4* r4) {
+  ldg256(res, reinterpret_cast<uint32_t*>(r4));
+  ldg256(res + 16, reinterpret_cast<uint32_t*>(r4 + 2));
 }
 
 // `res4`: the chunk's 32 residual values, already in registers (loaded one chunk ahead so their
@@ -120,6 +126,11 @@ __device__ __forceinline__ void conv_packed(const uint32_t* rr, const bf16* bias
 __device__ __forceinline__ void conv_chunk_packed(const uint32_t* rr, const bf16* bias, const uint4* res4,
                                                   uint32_t* y) {
   conv_packed<4>(rr, bias, res4, y);
+}
+
+__device__ __forceinline__ void store_chunk_packed32(bf16* o, const uint32_t* y) {
+  stg256(o, y);
+  stg256(o + 16, y + 8);
 }
 
 __device__ __forceinline__ void store_chunk_packed(bf16* o, const uint32_t* y) {

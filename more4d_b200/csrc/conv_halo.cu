@@ -99,7 +99,7 @@ __device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row
     uint4 rcur[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
-    if (has_res && c0 + 32 < NTC) load_res_chunk(p.residual + pix_off + c0 + 32, rnext);   // one chunk ahead
+    if (has_res && c0 + 32 < NTC) load_res_chunk32(p.residual + pix_off + c0 + 32, rnext);   // one chunk ahead
     uint32_t* y = yp + (c0 >> 1);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -126,16 +126,17 @@ __device__ __forceinline__ void rmsnorm_pass2(const ConvParams& p, long long pix
   const float sc = sqrtf(static_cast<float>(NTC));
   bf16* o = p.norm_out + pix_off;
 #pragma unroll
-  for (int c0 = 0; c0 < NTC; c0 += 8) {
-    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.norm_gamma + c0));
-    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
-    uint32_t ow[4];
+  for (int c0 = 0; c0 < NTC; c0 += 16) {            // 16 channels = one 256-bit store
+    const uint4 ga = __ldg(reinterpret_cast<const uint4*>(p.norm_gamma + c0));
+    const uint4 gb = __ldg(reinterpret_cast<const uint4*>(p.norm_gamma + c0 + 8));
+    const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    uint32_t ow[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 8; ++e) {
       ow[e] = rmsnorm_tail_bf16x2(yp[(c0 >> 1) + e], inv, sc, gw[e]);
       if (p.norm_silu) ow[e] = silu_bf16x2(ow[e]);
     }
-    *reinterpret_cast<uint4*>(o + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    stg256(o + c0, ow);
   }
 }
 
@@ -194,13 +195,13 @@ __device__ __forceinline__ void epilogue_vec(const ConvParams& p, uint32_t t_row
     if (p.out != nullptr) {                         // the raw output (x + h) some later shortcut consumes
 #pragma unroll
       for (int c0 = 0; c0 < NTC; c0 += 32)
-        store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, yp + (c0 >> 1));
+        store_chunk_packed32(reinterpret_cast<bf16*>(p.out) + pix_off + c0, yp + (c0 >> 1));
     }
     rmsnorm_pass2<NTC>(p, pix_off, yp, ss);
   } else {
 #pragma unroll
     for (int c0 = 0; c0 < NTC; c0 += 32)
-      store_chunk_packed(reinterpret_cast<bf16*>(p.out) + pix_off + c0, yp + (c0 >> 1));
+      store_chunk_packed32(reinterpret_cast<bf16*>(p.out) + pix_off + c0, yp + (c0 >> 1));
   }
 }
 
@@ -484,7 +485,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const char* rp = reinterpret_cast<const char*>(p.residual + pix_off);
         for (int bo = 0; bo < p.NT * 2; bo += 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + bo));
-        load_res_chunk(p.residual + pix_off, rnext);
+        if (p.vec_ok == 2) load_res_chunk32(p.residual + pix_off, rnext);
+        else load_res_chunk(p.residual + pix_off, rnext);
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -495,7 +497,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (p.NT == 96) epilogue_vec<96, true>(p, t_row, pix_off, 0, pix_ok, vec_res, rnext, release, acc, lane);
         else epilogue_vec<192, true>(p, t_row, pix_off, 0, pix_ok, vec_res, rnext, release, acc, lane);
         continue;                                      // the accumulators were released after pass 1
-      } else if (p.out_mode == 0 && p.vec_ok && n_base + p.NT <= p.Cout &&
+      } else if (p.out_mode == 0 && p.vec_ok == 2 && n_base + p.NT <= p.Cout &&
                  (p.NT == 96 || p.NT == 128 || p.NT == 192)) {    // warp-uniform
         // full-width tiles of the plain convs (96 / 128 / 192 / 2 x 192 channels): same drain-release-store
         if (p.NT == 96) epilogue_vec<96, false>(p, t_row, pix_off, n_base, pix_ok, vec_res, rnext, release, acc, lane);
@@ -565,10 +567,10 @@ int conv_halo_launch(const void* x, int T_in, int H_in, int W_in, const void* w_
   p.desc_mode = 0;
   M4D_REQUIRE(p.out_mode == 1 || p.n_split >= p.Cout, M4D_ERR_UNSUPPORTED);
   if (p.gn_partials != nullptr)
-    M4D_REQUIRE(p.norm_out == nullptr && p.vec_ok && p.out_mode == 0 && NT == 128 && p.Cout == 128 && p.n_tiles == 1,
+    M4D_REQUIRE(p.norm_out == nullptr && p.vec_ok == 2 && p.out_mode == 0 && NT == 128 && p.Cout == 128 && p.n_tiles == 1,
                 M4D_ERR_UNSUPPORTED);
   if (p.norm_out != nullptr) {
-    M4D_REQUIRE(p.vec_ok, M4D_ERR_ALIGN);
+    M4D_REQUIRE(p.vec_ok == 2 && (reinterpret_cast<uintptr_t>(p.norm_out) & 31) == 0, M4D_ERR_ALIGN);
     M4D_REQUIRE(p.norm_gamma != nullptr && p.out_mode == 0 && p.n_tiles == 1 && NT == p.Cout &&
                     (NT == 96 || NT == 192) && p.n_split >= p.Cout && p.out_C % 8 == 0,
                 M4D_ERR_UNSUPPORTED);

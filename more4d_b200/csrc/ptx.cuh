@@ -346,6 +346,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
+// ---- 256-bit global loads / stores (sm_100: LDG/STG.E.ENL2.256).  An epilogue thread owns a
+// contiguous run of one output row; written as 16-byte pieces every store covers HALF a 32-byte
+// sector and L1 forwards it as a partial write — twice the requests and twice the L1->L2 bytes
+// (measured on the conv epilogue: 3.87 GB leaving the SMs for 1.89 GB of output, stores stalled on
+// the LSU queue).  The address must be 32-byte aligned.
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg256_f(void* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* v) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg256_f(const void* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 // ---- packed bf16x2 arithmetic for the bf16-faithful row math (every intermediate of the
 // reference's bf16 tensors is rounded to bf16).  A product of two bf16 values is exact in fp32, and a
 // sum is exact whenever the smaller operand can still move the rounding, so mul/add.rn.bf16x2
