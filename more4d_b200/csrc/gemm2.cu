@@ -77,7 +77,23 @@ __device__ __forceinline__ void g2_epilogue_chunk(const uint32_t* r, const Gemm2
     float* orow = reinterpret_cast<float*>(ep.out) + m * ep.ldo + n0;
     const float* rrow = ep.res + m * ep.ldr + n0;
     const float* grow = ep.gate ? ep.gate + (m / ep.rows_per_batch) * ep.gate_bstride + n0 : nullptr;
-    if (full) {
+    if (full && ((reinterpret_cast<uintptr_t>(orow) | reinterpret_cast<uintptr_t>(rrow)) & 31) == 0) {
+      // 256-bit accesses: each covers a whole 32-byte sector of the fp32 row (16-byte pieces leave
+      // L1 as half-sector partial writes: twice the requests and twice the L1->L2 bytes)
+      float rr[32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ldg256_f(rrow + q * 8, rr + q * 8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 g = grow ? __ldg(reinterpret_cast<const float4*>(grow + q * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        rr[q * 4 + 0] += v[q * 4 + 0] * g.x;
+        rr[q * 4 + 1] += v[q * 4 + 1] * g.y;
+        rr[q * 4 + 2] += v[q * 4 + 2] * g.z;
+        rr[q * 4 + 3] += v[q * 4 + 3] * g.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) stg256_f(orow + q * 8, rr + q * 8);
+    } else if (full) {
       float4 rr[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) rr[q] = *reinterpret_cast<const float4*>(rrow + q * 4);
@@ -97,7 +113,13 @@ __device__ __forceinline__ void g2_epilogue_chunk(const uint32_t* r, const Gemm2
     }
   } else {
     bf16* orow = reinterpret_cast<bf16*>(ep.out) + m * ep.ldo + n0;
-    if (full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+    if (full && ((reinterpret_cast<uintptr_t>(orow) & 31) == 0)) {
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+      stg256(orow, o);
+      stg256(orow + 16, o + 8);
+    } else if (full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 o;
