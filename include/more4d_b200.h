@@ -277,6 +277,17 @@ int m4d_project_points(const float* points, const float* colors, const float* wo
                        const float* intrinsic, long long N, int H, int W, unsigned char* image,
                        unsigned char* mask, void* workspace, long long workspace_bytes, void* stream);
 
+/* The same for the V frames of a camera trajectory in ONE launch sequence (render_trajectory,
+ * scripts/inference/infer.py:398-444, calls render_with_project once per frame: launch-bound).
+ * points / colors: view v starts at element offset v * *_view_stride (0 = shared by all views);
+ * world2cam: HOST fp32 [V, 4, 4]; image [V, H, W, 3], mask [V, H, W].  Bit-identical to V calls of
+ * m4d_project_points. */
+long long m4d_project_views_workspace(long long N, int V, int H, int W);
+int m4d_project_views(const float* points, long long points_view_stride, const float* colors,
+                      long long colors_view_stride, const float* world2cam, const float* intrinsic,
+                      long long N, int V, int H, int W, unsigned char* image, unsigned char* mask,
+                      void* workspace, long long workspace_bytes, void* stream);
+
 /* Forward 3D-Gaussian-splatting render of V views in one launch sequence — `gs_render` /
  * `render_cuda` (MoRe4D/utils/gaussian_splatting.py:13-43,201-281) + the third-party
  * GaussianRasterizer it calls once per frame (README.md:60; scripts/inference/infer.py:260-273,

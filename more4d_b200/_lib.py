@@ -61,6 +61,8 @@ _SIGNATURES = {
     "m4d_gs_render": (c_int, [_P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _I, _F, _F, _F, _P, _P, _P, _L, _L, _P, _P]),
     "m4d_project_points_workspace": (c_longlong, [_L, _I, _I]),
     "m4d_project_points": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _L, _P]),
+    "m4d_project_views_workspace": (c_longlong, [_L, _I, _I, _I]),
+    "m4d_project_views": (c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P, _P, _P, _L, _P]),
 }
 
 _lib = None

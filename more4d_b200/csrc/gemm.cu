@@ -120,7 +120,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
           if (n0 + i < N) orow[i] = rrow[i] + v[i] * (grow ? grow[i] : 1.f);
       }
     } else {
-      if (full) {
+      if (full && (reinterpret_cast<uintptr_t>(orow) & 31) == 0) {
+        // 256-bit stores cover whole 32-byte sectors (16-byte pieces leave L1 as partial writes)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) stg256_f(orow + q * 8, v + q * 8);
+      } else if (full) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(orow + q * 4) =
@@ -138,7 +142,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const GemmEpi&
       for (int i = 0; i < 32; ++i)
         if (n0 + i < N) v[i] += __bfloat162float(rrow[i]);
     }
-    if (full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+    if (full && ((reinterpret_cast<uintptr_t>(orow) & 31) == 0)) {
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+      stg256(orow, o);
+      stg256(orow + 16, o + 8);
+    } else if (full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 o;

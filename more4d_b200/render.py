@@ -53,6 +53,39 @@ def project_points(world_points: torch.Tensor, extrinsic: torch.Tensor, intrinsi
     return image, mask
 
 
+def project_views(world_points: torch.Tensor, extrinsics: torch.Tensor, intrinsic: torch.Tensor,
+                  colors: torch.Tensor, H: int, W: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All V frames of a camera trajectory in one launch sequence (render_trajectory, infer.py:398-444,
+    calls render_with_project once per frame).  world_points / colors: [N, 3] shared by all views or
+    [V, N, 3] per view; extrinsics [V, 4, 4].  Returns device tensors (images uint8 [V, H, W, 3], masks
+    uint8 [V, H, W]), bit-identical to V calls of project_points."""
+    _lib.require_device()
+    if not world_points.is_cuda:
+        raise RuntimeError("more4d_b200.render: world_points must be a CUDA tensor (no CPU fallback)")
+    dev = world_points.device
+    pts = world_points.to(torch.float32).contiguous()
+    col = colors.to(device=dev, dtype=torch.float32).contiguous()
+    V = extrinsics.shape[0]
+    N = pts.shape[-2]
+    for name, t in (("world_points", pts), ("colors", col)):
+        if t.shape[-1] != 3 or t.shape[-2] != N or t.dim() not in (2, 3) or (t.dim() == 3 and t.shape[0] != V):
+            raise ValueError(f"more4d_b200.render: {name} must be [N, 3] or [V, N, 3]")
+    w2c = torch.linalg.inv(extrinsics.detach().to("cpu", torch.float32)).contiguous()
+    K = intrinsic.detach().to("cpu", torch.float32).contiguous()
+    lib = _lib.lib()
+    ws_bytes = lib.m4d_project_views_workspace(N, V, H, W)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    image = torch.empty(V, H, W, 3, device=dev, dtype=torch.uint8)
+    mask = torch.empty(V, H, W, device=dev, dtype=torch.uint8)
+    from . import ops
+    rc = lib.m4d_project_views(pts.data_ptr(), 3 * N if pts.dim() == 3 else 0, col.data_ptr(),
+                               3 * N if col.dim() == 3 else 0, w2c.data_ptr(), K.data_ptr(), N, V, H, W,
+                               image.data_ptr(), mask.data_ptr(), ws.data_ptr(), ws_bytes, ops._stream())
+    _lib.check(rc, "m4d_project_views")
+    ops._Stats.launches += 2
+    return image, mask
+
+
 def render_with_project(world_points: torch.Tensor, extrinsic: torch.Tensor, intrinsic: torch.Tensor,
                         colors: torch.Tensor, H: int, W: int, device=None) -> Tuple[np.ndarray, np.ndarray]:
     """infer.py:222-258: returns (image_proj uint8 [H, W, 3], mask bool [H, W]) as numpy arrays."""

@@ -69,3 +69,27 @@ def test_projection_fullsize_properties():
     # (3) against the oracle at full size
     ri, rm = P.render_with_project(pts.numpy(), torch.linalg.inv(ext).numpy(), K.numpy(), col.numpy(), H, W)
     assert np.array_equal(a_img, ri) and np.array_equal(a_mask, rm)
+
+
+def test_project_views_batched_equals_per_frame_calls():
+    """m4d_project_views: the V frames of a trajectory (moving points, moving camera) in one launch
+    sequence are bit-identical to V calls of render_with_project's kernel path."""
+    from more4d_b200 import render
+    H, W, V = 37, 53, 4
+    pts, col, ext, K = synth.point_cloud(H, W, 5, 0.1)
+    exts = []
+    for k in range(V):
+        e = ext.clone()
+        e[0, 3] += 0.04 * k
+        e[2, 3] -= 0.02 * k
+        exts.append(e)
+    exts = torch.stack(exts)
+    moving = torch.stack([pts + 0.01 * k for k in range(V)]).cuda()
+    img, mask = render.project_views(moving, exts, K, col.cuda(), H, W)
+    for k in range(V):
+        i1, m1 = render.project_points(moving[k], exts[k], K, col.cuda(), H, W)
+        assert torch.equal(img[k], i1) and torch.equal(mask[k], m1)
+    # shared points, several cameras
+    img2, _ = render.project_views(pts.cuda(), exts, K, col.cuda(), H, W)
+    i0, _ = render.project_points(pts.cuda(), exts[2], K, col.cuda(), H, W)
+    assert torch.equal(img2[2], i0)
