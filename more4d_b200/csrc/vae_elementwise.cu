@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256)
 rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, bf16* __restrict__ out,
                        long long pixels, int C, int do_silu) {
   __shared__ float part[RN_ITERS][256];
+  __shared__ float inv_s[RN_ITERS][256];
   const int lpp = C >> 3;                         // lanes (16-byte vectors) per pixel
   const int ppb = 256 / lpp;                      // pixels per block-iteration
   const int lp = threadIdx.x / lpp;               // local pixel
@@ -46,11 +47,15 @@ rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamm
   uint4 v[RN_ITERS];
   float ss[RN_ITERS];
 #pragma unroll
-  for (int it = 0; it < RN_ITERS; ++it) {
+  for (int it = 0; it < RN_ITERS; ++it) {            // all loads first: RN_ITERS requests in flight per thread
     const long long pix = pix0 + static_cast<long long>(it) * ppb;
+    v[it] = (active && pix < pixels) ? __ldcs(reinterpret_cast<const uint4*>(x + pix * C + lv * 8))
+                                     : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int it = 0; it < RN_ITERS; ++it) {
     ss[it] = 0.f;
-    if (active && pix < pixels) {
-      v[it] = *reinterpret_cast<const uint4*>(x + pix * C + lv * 8);
+    {
       const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -61,6 +66,18 @@ rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamm
     part[it][threadIdx.x] = ss[it];
   }
   __syncthreads();
+  // one thread per pixel folds the pixel's lpp partial sums (every thread doing it cost lpp shared
+  // loads per 8 channels: 6 per channel at C = 384) and publishes 1 / norm
+  if (active && lv == 0) {
+#pragma unroll
+    for (int it = 0; it < RN_ITERS; ++it) {
+      float tot = 0.f;
+      const float* pp = &part[it][lp * lpp];
+      for (int i = 0; i < lpp; ++i) tot += pp[i];
+      inv_s[it][lp] = 1.0f / fmaxf(bf16_round(sqrtf(tot)), 1e-12f);
+    }
+  }
+  __syncthreads();
   const uint4 g4 = active ? *reinterpret_cast<const uint4*>(gamma + lv * 8) : make_uint4(0, 0, 0, 0);
   const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
   const float sc = sqrtf(static_cast<float>(C));
@@ -68,11 +85,7 @@ rmsnorm_silu_cl_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamm
   for (int it = 0; it < RN_ITERS; ++it) {
     const long long pix = pix0 + static_cast<long long>(it) * ppb;
     if (!(active && pix < pixels)) continue;
-    float tot = 0.f;
-    const float* pp = &part[it][lp * lpp];
-    for (int i = 0; i < lpp; ++i) tot += pp[i];
-    const float nrm = fmaxf(bf16_round(sqrtf(tot)), 1e-12f);
-    const float inv = 1.0f / nrm;
+    const float inv = inv_s[it][lp];
     const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
     uint32_t o[4];
 #pragma unroll
