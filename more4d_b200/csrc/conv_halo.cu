@@ -92,8 +92,12 @@ template <int NTC, bool NORM>
 __device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row, long long pix_off, int n0,
                                              bool pix_ok, bool has_res, uint4* rnext, uint32_t* yp) {
   float ss = 0.f;
-  uint32_t rr[2][16];                              // TMEM loads in 16-column halves, double-buffered
-  tmem_ld16(t_row, rr[0]);
+  // TMEM loads double-buffered: 32-column chunks while the registers allow it (NTC <= 128: half as
+  // many load round trips per tile), 16-column halves at 192 channels (96 packed words are live)
+  constexpr int TW = NTC <= 128 ? 32 : 16;
+  uint32_t rr[2][TW];
+  if (TW == 32) tmem_ld32(t_row, rr[0]);
+  else tmem_ld16(t_row, rr[0]);
 #pragma unroll
   for (int c0 = 0; c0 < NTC; c0 += 32) {
     uint4 rcur[4];
@@ -101,13 +105,20 @@ __device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row
     for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
     if (has_res && c0 + 32 < NTC) load_res_chunk32(p.residual + pix_off + c0 + 32, rnext);   // one chunk ahead
     uint32_t* y = yp + (c0 >> 1);
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int cc = c0 + hf * 16;
-      const int cur = (cc >> 4) & 1;
+    if (TW == 32) {
+      const int cur = (c0 >> 5) & 1;
       tmem_ld_wait();
-      if (cc + 16 < NTC) tmem_ld16(t_row + cc + 16, rr[cur ^ 1]);
-      conv_packed<2>(rr[cur], p.bias ? p.bias + n0 + cc : nullptr, has_res ? rcur + 2 * hf : nullptr, y + hf * 8);
+      if (c0 + 32 < NTC) tmem_ld32(t_row + c0 + 32, rr[cur ^ 1]);
+      conv_packed<4>(rr[cur], p.bias ? p.bias + n0 + c0 : nullptr, has_res ? rcur : nullptr, y);
+    } else {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cc = c0 + hf * 16;
+        const int cur = (cc >> 4) & 1;
+        tmem_ld_wait();
+        if (cc + 16 < NTC) tmem_ld16(t_row + cc + 16, rr[cur ^ 1]);
+        conv_packed<2>(rr[cur], p.bias ? p.bias + n0 + cc : nullptr, has_res ? rcur + 2 * hf : nullptr, y + hf * 8);
+      }
     }
     if (NORM) {
 #pragma unroll
