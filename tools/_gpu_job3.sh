@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 1200 ncu --nvtx --nvtx-include "m4d_timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 1 --warmup 1 --no-vae --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
-wc -l gpurun_out/launches_r02.csv; tail -2 gpurun_out/launches_bench.log | cut -c1-300
+(timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_vae_gpu.py -m gpu -q -x -k "fused_groupnorm or row_kernels or thin or conv" 2>&1 | tail -15) > gpurun_out/sanitizer_vae.log
+tail -15 gpurun_out/sanitizer_vae.log
+(timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "two_segments or guard_paths or rmsnorm or layernorm" 2>&1 | tail -15) > gpurun_out/sanitizer_k.log
+tail -15 gpurun_out/sanitizer_k.log
