@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-(timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_vae_gpu.py -m gpu -q -x -k "fused_groupnorm or row_kernels or thin or conv" 2>&1 | tail -15) > gpurun_out/sanitizer_vae.log
-tail -15 gpurun_out/sanitizer_vae.log
-(timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "two_segments or guard_paths or rmsnorm or layernorm" 2>&1 | tail -15) > gpurun_out/sanitizer_k.log
-tail -15 gpurun_out/sanitizer_k.log
+timeout 400 python tools/bench_project.py > gpurun_out/project_r02.json 2> gpurun_out/project_r02.err
+cat gpurun_out/project_r02.json | python -c "import json,sys; d=json.load(sys.stdin); print(d['gs_render']); print([ (r['frame'], r['gpu_ms_per_frame'], r['batched_gpu_ms_per_frame']) for r in d['results']])"
+tail -3 gpurun_out/project_r02.err

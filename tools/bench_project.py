@@ -59,7 +59,38 @@ def main():
                     "batched_gpu_ms_per_frame": ms_batched, "batched_frames_per_s": 1e3 / ms_batched,
                     "batched_algorithmic_GBps": nbytes / ms_batched / 1e6, "cpu_oracle_ms_per_frame": cpu_ms,
                     "note": "includes the host-side 4x4 inverse and workspace allocation of the public call"})
-    print(json.dumps({"workload": "render_with_project z-buffer, synthetic point clouds", "results": out}))
+    # 3DGS forward rasteriser at BASELINE config 5: 368 x 512 = 188 416 gaussians (scale 1e-4, identity
+    # rotation, opacity 1: infer.py:263-270), all frames of the trajectory in one launch sequence
+    gs = []
+    for (H, W) in ((368, 512),):
+        pts, col, ext, K = synth.point_cloud(H, W, 0, 0.05)
+        V = a.frames
+        exts = torch.stack([ext.clone() for _ in range(V)])
+        for k in range(V):
+            exts[k, 0, 3] += 0.002 * k
+        moving = torch.stack([pts + 0.001 * k for k in range(V)]).cuda()
+        c = (col / 255.0).cuda()
+        args = (torch.ones(len(pts)), torch.tensor([1e-4] * 3), torch.tensor([0.0, 0.0, 0.0, 1.0]))
+        render.gs_render_views(moving, c, *args, exts, K, H, W)
+        torch.cuda.synchronize()
+        s, t = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record()
+        img = render.gs_render_views(moving, c, *args, exts, K, H, W)
+        t.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(t)
+        from oracle import gs_oracle as G
+        import numpy as np
+        t0 = time.perf_counter()
+        G.render(pts.numpy()[:20000], (col / 255.0).numpy()[:20000], np.ones(20000, np.float32), [1e-4] * 3, [0, 0, 0, 1],
+                 ext.numpy(), K.numpy(), H, W)
+        cpu_ms = (time.perf_counter() - t0) * 1e3 * len(pts) / 20000
+        gs.append({"frame": f"{H}x{W}", "gaussians": len(pts), "views": V, "gpu_ms_total": ms,
+                   "gpu_ms_per_frame": ms / V, "frames_per_s": V * 1e3 / ms, "finite": bool(torch.isfinite(img).all()),
+                   "cpu_oracle_ms_per_frame_extrapolated": cpu_ms,
+                   "note": "cpu: numpy oracle on 20 000 of the gaussians, scaled linearly"})
+    print(json.dumps({"workload": "render_with_project z-buffer, synthetic point clouds", "results": out,
+                      "gs_render": gs}))
 
 
 if __name__ == "__main__":
