@@ -175,6 +175,19 @@ class AutoencoderKLWan(nn.Module):
 
     def _conv(self, x: Tensor, name: str, kernel, cout: int, pad, **kw) -> Tensor:
         w = self._p(name + ".weight")
+        if tuple(kernel) == (1, 1, 1) and not (set(kw) - {"out"}) and w.shape[1] == x.shape[-1] \
+                and x.is_contiguous() and x.shape[-1] % 8 == 0:
+            # a 1x1x1 convolution over channels-last pixels IS a row-major GEMM [pixels, Cin] x [Cout, Cin]^T
+            # (shortcuts vae:204-205, conv1 / conv2 vae:509-510): the 2-CTA GEMM with its double-buffered,
+            # 256-bit epilogue instead of the per-tap conv kernel (output-bound at K = 96: 6.0 -> 2 ms)
+            out = kw.get("out")
+            T, H, W, _ = x.shape
+            if out is None:
+                out = torch.empty(T, H, W, cout, device=x.device, dtype=BF16)
+            if out.is_contiguous() and tuple(out.shape) == (T, H, W, cout):
+                ops.linear(x.view(T * H * W, -1), w.view(cout, -1), self._p(name + ".bias"),
+                           out=out.view(T * H * W, cout))
+                return out
         mult = 16 if x.shape[-1] % 32 else 32               # thin (3 -> 16 channel) inputs
         return ops.conv_cl(x, self._packed.get(name, w, mult), self._p(name + ".bias"), cout, kernel, pad=pad, **kw)
 

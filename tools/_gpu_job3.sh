@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 400 python tools/bench_project.py > gpurun_out/project_r02.json 2> gpurun_out/project_r02.err
-cat gpurun_out/project_r02.json | python -c "import json,sys; d=json.load(sys.stdin); print(d['gs_render']); print([ (r['frame'], r['gpu_ms_per_frame'], r['batched_gpu_ms_per_frame']) for r in d['results']])"
-tail -3 gpurun_out/project_r02.err
+(timeout 600 python -m pytest tests/test_vae_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/pytest_k.log
+cat gpurun_out/pytest_k.log
+timeout 300 python tools/vae_trace.py > gpurun_out/vae_trace_r02i.md 2> gpurun_out/vae_trace.err
+head -18 gpurun_out/vae_trace_r02i.md; grep "linear\|(1,1,1)" gpurun_out/vae_trace_r02i.md | head; tail -3 gpurun_out/vae_trace.err
