@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_vae_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/pytest_k.log
-cat gpurun_out/pytest_k.log
-timeout 300 python tools/vae_trace.py > gpurun_out/vae_trace_r02i.md 2> gpurun_out/vae_trace.err
-head -18 gpurun_out/vae_trace_r02i.md; grep "linear\|(1,1,1)" gpurun_out/vae_trace_r02i.md | head; tail -3 gpurun_out/vae_trace.err
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe_probe tools/pipe_probe.cu && /tmp/pipe_probe > gpurun_out/pipe_probe_r02b.log 2>&1
+grep -i "f16\|bf16\|MUFU\|mix" gpurun_out/pipe_probe_r02b.log

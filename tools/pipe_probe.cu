@@ -57,6 +57,16 @@ __global__ void probe(float* out, long long* clocks, float seed) {
             add2(a[2 * i], a[2 * i + 1], seed, 0.25f);
           }
         }
+        if (KIND == 10) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));                                           // MUFU.EX2 on a packed fp16 pair
+        if (KIND == 11) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(a[8 + i]));           // F2FP to fp16x2
+        if (KIND == 12) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));                     // HADD2
+        if (KIND == 13) {                                                  // fp16 softmax mix per pair: FFMA2, F2FP.F16, EX2.F16x2, HADD2
+          fma2(a[2 * i], a[2 * i + 1], a[2 * i], a[2 * i + 1], seed, 0.5f);
+          asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[2 * i]), "f"(a[2 * i + 1]));
+          asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+          asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(u[(i + 4) & 7]) : "r"(u[i]));
+        }
+        if (KIND == 14) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u[i]));                                      // MUFU.EX2 on a packed bf16 pair
         if (KIND == 8) asm volatile("fma.rn.sat.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(a[8 + i]), "f"(seed));             // FFMA.SAT
         if (KIND == 9) asm volatile("fma.rm.ftz.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(a[8 + i]), "f"(seed));             // FFMA.RM
       }
@@ -101,6 +111,11 @@ int main() {
   run<8>("FFMA.SAT", 1);
   run<9>("FFMA.RM", 1);
   run<7>("mix / slot (avg of FFMA2,EX2,EX2,F2FP | FFMA2,FADD2)", 3);
+  run<10>("MUFU.EX2 f16x2 (ex2.approx.f16x2)", 1);
+  run<14>("MUFU.EX2 bf16x2", 1);
+  run<11>("F2FP f16x2 (cvt.rn.f16x2.f32)", 1);
+  run<12>("HADD2 (add.rn.f16x2)", 1);
+  run<13>("fp16 softmax mix / instr (FFMA2,F2FP,EX2.F16x2,HADD2)", 4);
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
