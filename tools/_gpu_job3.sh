@@ -1,3 +1,11 @@
 mkdir -p gpurun_out
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe_probe tools/pipe_probe.cu && /tmp/pipe_probe > gpurun_out/pipe_probe_r02b.log 2>&1
-grep -i "f16\|bf16\|MUFU\|mix" gpurun_out/pipe_probe_r02b.log
+rm -f gpurun_out/bench_r02_other_workloads.jsonl
+for w in 480p-14b 720p-1.3b 480p-1.3b visim-368p-14b; do
+  timeout 400 python bench.py --workload $w --no-cpu-baseline --no-vae 2> gpurun_out/other_$w.err >> gpurun_out/bench_r02_other_workloads.jsonl
+  tail -2 gpurun_out/other_$w.err
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/bench_r02_other_workloads.jsonl'):
+    d=json.loads(l); print(d['config']['workload'][:40], round(d['value'],4), round(d['ms_per_step'],1), round(d['roofline']['frac'],3), d['kernel_class_ms']['gemm_tflops'])
+PY
