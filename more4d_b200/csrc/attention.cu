@@ -40,6 +40,7 @@ constexpr int A_XCHG_BYTES = 2 * 4 * 2 * 32 * 4;   // MODE 2: one float per (til
 constexpr int A_SMEM_BYTES = (A_NQ + A_KS + A_VS) * A_TILE_BYTES + 256 + 1024 + A_XCHG_BYTES;
 
 constexpr float A_RESCALE_THRESHOLD = 8.0f;   // log2 units
+constexpr int A_PERSIST_MAX_KEYS = 2048;      // key ranges up to 16 tiles run on persistent CTAs
 constexpr int A_DEFAULT_PP = 2;               // pairs (of 8) whose 2^x runs on the FMA pipe
 constexpr int A_DEFAULT_MODE = 1;             // 1: sum-guarded speculative reference
 constexpr float A_SUM_GUARD = 65536.0f;       // MODE 1: a half tile whose row sum reaches 2^16 moves the reference
@@ -160,6 +161,8 @@ struct AttnParams {
   // epilogue adds the second segment onto the stored bf16 — one Q load, one prologue, one epilogue
   // pair instead of two launches that each run 3-4 key tiles.  0 = one segment.
   int seg_tiles;
+  // PERSIST kernels: work items (q block, head, batch), q block fastest; n_items = n_qblk * heads * B
+  int n_qblk, n_items;
   // scatter epilogue (sequence-parallel exchange fused into the attention epilogue): query row l
   // is stored to out_scatter[l / scatter_rows] at row l % scatter_rows — the destinations are
   // the ranks' receive buffers (peer memory), one launch serves all of them
@@ -173,7 +176,12 @@ struct AttnParams {
 // profiles/attn_variant_sweep_r01.log): one mbarrier arrival per warp instead of per thread
 // (-4 %), P in 1 or 4 slices, 64-key steps with a double-buffered S (-25 %: N=64 QK MMAs are
 // shared-memory bound), two threads per row (16 softmax warps share the MUFU: -9 %).
-template <int PP, int MODE>
+// PERSIST: one CTA per SM loops over work items (q block, head, batch).  For the short key ranges of
+// the cross-attention (7 key tiles: ~10 us of tensor work) a CTA per item spent ~26 us on launch,
+// barrier / TMEM set-up, the first loads and the epilogue with the tensor pipe idle (36 us per CTA,
+// 425 TF/s).  Here the next item's Q / K / V loads and its first QK^T are issued while the softmax
+// warps are still in the previous item's epilogue; barrier phases run on (item, tile) counters.
+template <int PP, int MODE, bool PERSIST = false>
 __global__ void __launch_bounds__(MODE == 2 ? A_THREADS_SPLIT : A_THREADS, 1)
 attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -192,16 +200,36 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* s_full = v_empty + A_VS;    // 2
   uint64_t* p_ready = s_full + 2;       // per tile t: [4t + 0/1] P halves ready, [4t + 2] PV of the first half done
   uint64_t* o_final = p_ready + 8;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  uint64_t* q_empty = o_final + 2;      // 1   PERSIST: every QK^T of the item has been executed
+  uint64_t* o_free = q_empty + 1;       // 2   PERSIST: the item's epilogue has drained O_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
   float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // MODE 2 partner exchange
 
   constexpr int NSW = (MODE == 2) ? 16 : 8;       // softmax warps; then TMA, MMA, TMEM-allocator warps
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  static_assert(!(PERSIST && MODE == 2), "the split-column variant is not persistent");
+  const int n_iter = PERSIST ? (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                   static_cast<int>(gridDim.x)
+                             : 1;
+  auto decode = [&](int it, int& q_blk_, int& head_, int& b_) {
+    if (PERSIST) {
+      const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      q_blk_ = item % p.n_qblk;
+      const int r = item / p.n_qblk;
+      head_ = r % p.heads;
+      b_ = r / p.heads;
+    } else {
+      q_blk_ = blockIdx.x;
+      head_ = blockIdx.y;
+      b_ = blockIdx.z;
+    }
+  };
+  int q_blk, head, b;
+  decode(0, q_blk, head, b);
 
   int kv_len = p.Lk;
-  if (p.k_lens != nullptr) {
+  if (!PERSIST && p.k_lens != nullptr) {           // persistent launches take no k_lens (checked on the host)
     int kl = p.k_lens[b];
     kv_len = kl < kv_len ? kl : kv_len;
   }
@@ -227,7 +255,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&s_full[t], 1);
       for (int i = 0; i < 4; ++i) mbar_init(&p_ready[4 * t + i], i == 2 ? 1 : 128);   // [2]: pv_half, by commit
       mbar_init(&o_final[t], 1);
+      mbar_init(&o_free[t], 128);
     }
+    mbar_init(q_empty, 1);
     fence_mbar_init();
   }
   if (warp == NSW + 2) tmem_alloc<512>(tmem_slot);
@@ -240,23 +270,30 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ------------------------------------------------------------------ data movement + MMA
     if (MODE != 2) reg_dec<80>();
     if (warp == NSW && lane == 0) {
-      mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
-      for (int t = 0; t < A_NQ; ++t)
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sQ + t * A_TILE_BYTES + h * A_HALF_BYTES, &tmQ, q_full, h * 64, head,
-                      q_blk * (A_NQ * A_BQ) + t * A_BQ, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int sk = j % A_KS, sv = j % A_VS;
-        mbar_wait(&k_empty[sk], ((j / A_KS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[sk], A_TILE_BYTES);
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sK + sk * A_TILE_BYTES + h * A_HALF_BYTES, &tmK, &k_full[sk], h * 64, head,
-                      j * A_BKV, b);
-        mbar_wait(&v_empty[sv], ((j / A_VS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[sv], A_TILE_BYTES);
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sV + sv * A_TILE_BYTES + h * A_HALF_BYTES, &tmV, &v_full[sv], h * 64, head,
-                      j * A_BKV, b);
+      for (int it = 0; it < n_iter; ++it) {
+        if (PERSIST) {
+          decode(it, q_blk, head, b);
+          mbar_wait(q_empty, (it & 1) ^ 1);        // the previous item's QK^T MMAs have read Q
+        }
+        mbar_arrive_expect_tx(q_full, A_NQ * A_TILE_BYTES);
+        for (int t = 0; t < A_NQ; ++t)
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d(sQ + t * A_TILE_BYTES + h * A_HALF_BYTES, &tmQ, q_full, h * 64, head,
+                        q_blk * (A_NQ * A_BQ) + t * A_BQ, b);
+        for (int j = 0; j < n_kv; ++j) {
+          const int g = it * n_kv + j;             // running tile counter: ring slot and parity
+          const int sk = g % A_KS, sv = g % A_VS;
+          mbar_wait(&k_empty[sk], ((g / A_KS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[sk], A_TILE_BYTES);
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d(sK + sk * A_TILE_BYTES + h * A_HALF_BYTES, &tmK, &k_full[sk], h * 64, head,
+                        j * A_BKV, b);
+          mbar_wait(&v_empty[sv], ((g / A_VS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[sv], A_TILE_BYTES);
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d(sV + sv * A_TILE_BYTES + h * A_HALF_BYTES, &tmV, &v_full[sv], h * 64, head,
+                        j * A_BKV, b);
+        }
       }
     } else if (warp == NSW + 1) {
       // The whole warp runs this loop converged and ONE elected lane issues: operands then live
@@ -286,11 +323,13 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // O_t += P_t[:, slice] V[slice, :] — P arrives in NS key-slices so the first PV MMAs
       // overlap the exponentials of the later slices
       constexpr int NS = 2;
-      auto issue_pv_tile = [&](int t, int sv, int j, bool leader) {   // whole warp
+      auto issue_pv_tile = [&](int t, int sv, int j, int g, int it, bool leader) {   // whole warp
         const uint32_t b_lo = v_lo + sv * (A_TILE_BYTES >> 4);
+        // PERSIST: the first PV of an item overwrites O_t — the previous item's epilogue must be done
+        if (PERSIST && j == 0 && it > 0) mbar_wait(&o_free[t], (it - 1) & 1);
 #pragma unroll
         for (int sl = 0; sl < NS; ++sl) {
-          mbar_wait(&p_ready[4 * t + sl], j & 1);
+          mbar_wait(&p_ready[4 * t + sl], g & 1);
           tc_fence_after();
           if (leader) {
 #pragma unroll
@@ -308,46 +347,52 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       };
 
       const bool leader = elect_one();
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (leader) {
-        issue_qk(0, 0);
-        umma_commit(&s_full[0]);
-        issue_qk(1, 0);
-        umma_commit(&s_full[1]);
-        umma_commit(&k_empty[0]);
-      }
-      __syncwarp();
-      for (int j = 0; j < n_kv; ++j) {
-        const int sv = j % A_VS;
-        const bool last = (j + 1 == n_kv);
-        const int sk = (j + 1) % A_KS;
-        mbar_wait(&v_full[sv], (j / A_VS) & 1);
-        issue_pv_tile(0, sv, j, leader);
-        if (!last) mbar_wait(&k_full[sk], ((j + 1) / A_KS) & 1);
+      for (int it = 0; it < n_iter; ++it) {
+        const int g0 = it * n_kv;
+        mbar_wait(q_full, it & 1);
+        mbar_wait(&k_full[g0 % A_KS], (g0 / A_KS) & 1);
         tc_fence_after();
         if (leader) {
-          if (last) {
-            umma_commit(&o_final[0]);
-          } else {
-            issue_qk(0, sk);
-            umma_commit(&s_full[0]);
-          }
+          // S_t is free: the previous item's last PV_t was issued before this and executes in order
+          issue_qk(0, g0 % A_KS);
+          umma_commit(&s_full[0]);
+          issue_qk(1, g0 % A_KS);
+          umma_commit(&s_full[1]);
+          umma_commit(&k_empty[g0 % A_KS]);
         }
         __syncwarp();
-        issue_pv_tile(1, sv, j, leader);
-        if (leader) {
-          umma_commit(&v_empty[sv]);
-          if (last) {
-            umma_commit(&o_final[1]);
-          } else {
-            issue_qk(1, sk);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[sk]);
+        for (int j = 0; j < n_kv; ++j) {
+          const int g = g0 + j;
+          const int sv = g % A_VS;
+          const bool last = (j + 1 == n_kv);
+          const int sk = (g + 1) % A_KS;
+          if (PERSIST && last && leader) umma_commit(q_empty);   // all QK^T of this item are issued
+          mbar_wait(&v_full[sv], (g / A_VS) & 1);
+          issue_pv_tile(0, sv, j, g, it, leader);
+          if (!last) mbar_wait(&k_full[sk], ((g + 1) / A_KS) & 1);
+          tc_fence_after();
+          if (leader) {
+            if (last) {
+              umma_commit(&o_final[0]);
+            } else {
+              issue_qk(0, sk);
+              umma_commit(&s_full[0]);
+            }
           }
+          __syncwarp();
+          issue_pv_tile(1, sv, j, g, it, leader);
+          if (leader) {
+            umma_commit(&v_empty[sv]);
+            if (last) {
+              umma_commit(&o_final[1]);
+            } else {
+              issue_qk(1, sk);
+              umma_commit(&s_full[1]);
+              umma_commit(&k_empty[sk]);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (MODE == 2) {
@@ -554,6 +599,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     asm volatile("mov.u32 %0, %1;" : "=r"(pr0) : "r"(smem_u32(&p_ready[4 * t + 0])));
     float m_used = -INFINITY;                      // reference, in logit units (r = m_used * c)
     float l_sum = 0.f;
+    bool row_ok = false;                           // per work item (set at the top of the item loop)
+    bool row32 = false;                            // the output row is 32-byte aligned
+    bf16* orow = nullptr;
 
     // O *= f, by 32-column chunks (rare path)
     auto rescale_o = [&](float f) {
@@ -569,10 +617,9 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_st_wait();
     };
 
-    const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
-    const bool row_ok = q_row < p.Lq;
-    bf16* orow;
-    {
+    auto locate_rows = [&]() {
+      const int q_row = q_blk * (A_NQ * A_BQ) + t * A_BQ + row;
+      row_ok = q_row < p.Lq;
       bf16* obase = p.out;
       int o_row = q_row;
       if (p.scatter_rows > 0 && row_ok) {
@@ -582,48 +629,74 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       orow = obase + static_cast<long long>(b) * p.out_stride_b +
              static_cast<long long>(o_row) * p.out_stride_l + head * A_D;
-    }
-    // O / l -> bf16 -> global (accum: out = bf16(bf16(o) + out))
-    auto store_o = [&](float inv_l, bool accum) {
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t o[32];
-        tmem_ld32(tO + cc * 32, o);
+      row32 = (reinterpret_cast<uintptr_t>(orow) & 31) == 0;
+    };
+    // O / l -> bf16 -> global (accum: out = bf16(bf16(o) + out)).  All four 32-column TMEM loads are
+    // issued before the first wait, and `prev` — the row's previous output for the accumulate forms,
+    // loaded by the caller BEFORE it waits for the last PV — keeps the global-load latency out of the
+    // epilogue (both were the top stalls of the cross-attention: profiles/cross_attn_r02.md).
+    // 256-bit accesses when the row is 32-byte aligned (whole sectors, ptx.cuh).
+    auto load_prev = [&](uint32_t* prev) {
+      if (!row_ok) return;
+      if (row32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ldg256(orow + q * 16, prev + q * 8);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const uint4 w = *reinterpret_cast<const uint4*>(orow + q * 8);
+          prev[q * 4 + 0] = w.x; prev[q * 4 + 1] = w.y; prev[q * 4 + 2] = w.z; prev[q * 4 + 3] = w.w;
+        }
+      }
+    };
+    auto store_o = [&](float inv_l, const uint32_t* prev) {     // prev == nullptr: plain store
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {             // 64 columns at a time: two TMEM loads in flight
+        uint32_t o[64];
+        tmem_ld32(tO + hf * 64, o);
+        tmem_ld32(tO + hf * 64 + 32, o + 32);
         tmem_ld_wait();
+        reg_fence32(o);
+        reg_fence32(o + 32);
         if (row_ok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
+          for (int q = 0; q < 4; ++q) {            // 16 channels per step
+            uint32_t w[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[q * 8 + e]) * inv_l;
-            uint4* dst = reinterpret_cast<uint4*>(orow + cc * 32 + q * 8);
-            if (accum) {
-              const uint4 prev = *dst;
-              const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] = bf16_round(v[2 * e]) + __uint_as_float(w[e] << 16);
-                v[2 * e + 1] = bf16_round(v[2 * e + 1]) + __uint_as_float(w[e] & 0xFFFF0000u);
+            for (int e = 0; e < 8; ++e) {
+              float v0 = __uint_as_float(o[q * 16 + 2 * e]) * inv_l, v1 = __uint_as_float(o[q * 16 + 2 * e + 1]) * inv_l;
+              if (prev != nullptr) {
+                v0 = bf16_round(v0) + bf16_lo(prev[hf * 32 + q * 8 + e]);
+                v1 = bf16_round(v1) + bf16_hi(prev[hf * 32 + q * 8 + e]);
               }
+              w[e] = pack_bf16(v0, v1);
             }
-            uint4 ov;
-            ov.x = pack_bf16(v[0], v[1]);
-            ov.y = pack_bf16(v[2], v[3]);
-            ov.z = pack_bf16(v[4], v[5]);
-            ov.w = pack_bf16(v[6], v[7]);
-            *dst = ov;
+            bf16* dst = orow + hf * 64 + q * 16;
+            if (row32) {
+              stg256(dst, w);
+            } else {
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
           }
         }
       }
     };
 
+    for (int it = 0; it < n_iter; ++it) {
+    if (PERSIST) decode(it, q_blk, head, b);
+    locate_rows();
+    m_used = -INFINITY;
+    l_sum = 0.f;
+    const int g0 = it * n_kv;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
+      const int g = g0 + j;                        // running tile counter: barrier parities
+      mbar_wait(&s_full[t], g & 1);
       tc_fence_after();
       if (__builtin_expect(j > 0 && j == p.seg_tiles, 0)) {
         // segment boundary: "S_t(j) ready" implies PV_t(j-1) has finished, so O holds the whole
         // first segment; the next PV starts a fresh accumulator (MMA warp) — finish this one
-        store_o(1.0f / l_sum, p.accumulate != 0);
+        store_o(1.0f / l_sum, nullptr);             // (two segments never come with accumulate: host check)
         m_used = -INFINITY;
         l_sum = 0.f;
       }
@@ -633,31 +706,47 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int valid = kv_len - j * A_BKV;        // keys of this tile that exist
       float l0 = 0.f, l1 = 0.f;
       if (MODE == 1) {
-        // ---- first half, speculative
-        tmem_ld32(tS + 0, s + 0);
-        tmem_ld_wait();                            // chunk 0 has landed
-        tmem_ld32(tS + 32, s + 32);                // in flight while chunk 0 is processed
-        tmem_ld32(tS + 64, s + 64);
-        tmem_ld32(tS + 96, s + 96);
-        reg_fence32(s + 0);
-        if (__builtin_expect(valid < 32, 0)) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= valid) s[i] = 0xFF800000u;    // -inf
-        }
         float neg_mc = -m_used * c;
-        exp_pipe<PP, 0, 16>(s, ph, c, neg_mc, l0, l1);
-        tmem_ld_wait();
-        reg_fence32(s + 32);
-        reg_fence32(s + 64);
-        reg_fence32(s + 96);
-        if (__builtin_expect(valid < A_BKV, 0)) {
+        bool exact = true;                         // a segment's first tile has no reference to speculate with
+        if (__builtin_expect(!first, 1)) {
+          // ---- first half, speculative
+          tmem_ld32(tS + 0, s + 0);
+          tmem_ld_wait();                          // chunk 0 has landed
+          tmem_ld32(tS + 32, s + 32);              // in flight while chunk 0 is processed
+          tmem_ld32(tS + 64, s + 64);
+          tmem_ld32(tS + 96, s + 96);
+          reg_fence32(s + 0);
+          if (__builtin_expect(valid < 32, 0)) {
 #pragma unroll
-          for (int i = 32; i < 128; ++i)
-            if (i >= valid) s[i] = 0xFF800000u;
+            for (int i = 0; i < 32; ++i)
+              if (i >= valid) s[i] = 0xFF800000u;  // -inf
+          }
+          exp_pipe<PP, 0, 16>(s, ph, c, neg_mc, l0, l1);
+          tmem_ld_wait();
+          reg_fence32(s + 32);
+          reg_fence32(s + 64);
+          reg_fence32(s + 96);
+          if (__builtin_expect(valid < A_BKV, 0)) {
+#pragma unroll
+            for (int i = 32; i < 128; ++i)
+              if (i >= valid) s[i] = 0xFF800000u;
+          }
+          exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
+          exact = __any_sync(0xffffffffu, !(l0 + l1 < A_SUM_GUARD));
+        } else {
+          // (the exact path below loads the first half itself; the second half is taken from here)
+          tmem_ld32(tS + 64, s + 64);
+          tmem_ld32(tS + 96, s + 96);
+          tmem_ld_wait();
+          reg_fence32(s + 64);
+          reg_fence32(s + 96);
+          if (__builtin_expect(valid < A_BKV, 0)) {
+#pragma unroll
+            for (int i = 64; i < 128; ++i)
+              if (i >= valid) s[i] = 0xFF800000u;
+          }
         }
-        exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
-        if (__builtin_expect(__any_sync(0xffffffffu, first || !(l0 + l1 < A_SUM_GUARD)), 0)) {
+        if (__builtin_expect(exact, 0)) {
           // exact path for the whole tile: S is intact (nothing of this tile has been stored);
           // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled
           const bool mine = first || !(l0 + l1 < A_SUM_GUARD);
@@ -703,7 +792,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           // the first half is with the tensor pipe at the old reference: wait for its MMAs,
           // then move the reference (true max of the second half), rescale O / l, redo the half
           const bool mine = !(h0 + h1 < A_SUM_GUARD);
-          mbar_wait(&p_ready[4 * t + 2], j & 1);
+          mbar_wait(&p_ready[4 * t + 2], g & 1);
           tc_fence_after();
           float mxr = -INFINITY;
 #pragma unroll 1
@@ -796,9 +885,22 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
 
     // ---- epilogue: O / l -> bf16 -> global
-    mbar_wait(&o_final[t], 0);
-    tc_fence_after();
-    store_o(1.0f / l_sum, p.accumulate != 0 || p.seg_tiles > 0);
+    if (p.accumulate != 0 || p.seg_tiles > 0) {
+      uint32_t prev[64];
+      load_prev(prev);                             // in flight while the last PV finishes
+      mbar_wait(&o_final[t], it & 1);
+      tc_fence_after();
+      store_o(1.0f / l_sum, prev);
+    } else {
+      mbar_wait(&o_final[t], it & 1);
+      tc_fence_after();
+      store_o(1.0f / l_sum, nullptr);
+    }
+    if (PERSIST) {                                 // O_t may be overwritten by the next item's first PV
+      tc_fence_before();
+      mbar_arrive(&o_free[t]);
+    }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -826,7 +928,8 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
   M4D_REQUIRE(q && k && v && out, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(head_dim == A_D, M4D_ERR_UNSUPPORTED);          // d = 128 is the Wan2.1 invariant
-  M4D_REQUIRE(seg_len >= 0 && seg_len % A_BKV == 0 && seg_len < Lk && (seg_len == 0 || (k_lens == nullptr && n_scatter == 0)),
+  M4D_REQUIRE(seg_len >= 0 && seg_len % A_BKV == 0 && seg_len < Lk &&
+                  (seg_len == 0 || (k_lens == nullptr && n_scatter == 0 && accumulate == 0)),
               M4D_ERR_UNSUPPORTED);
   M4D_REQUIRE(heads <= 65535 && B <= 65535, M4D_ERR_BAD_SHAPE);
   M4D_REQUIRE(q_stride_l >= heads * A_D && kv_stride_l >= heads * A_D &&
@@ -854,10 +957,17 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
 
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams) = attn_fwd_d128_kernel<A_DEFAULT_PP, A_DEFAULT_MODE>;
   int threads = A_DEFAULT_MODE == 2 ? A_THREADS_SPLIT : A_THREADS;
+  // short key ranges (the cross-attention: 769 keys = 7 tiles): persistent CTAs, one per SM
+  const int n_qblk = (Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ);
+  const long long n_items = static_cast<long long>(n_qblk) * heads * B;
+  bool persist = A_DEFAULT_MODE != 2 && k_lens == nullptr && Lk <= A_PERSIST_MAX_KEYS && n_items > sm_count() &&
+                 n_items < (1ll << 30);
+  if (persist) kern = attn_fwd_d128_kernel<A_DEFAULT_PP, A_DEFAULT_MODE == 2 ? 1 : A_DEFAULT_MODE, true>;
 #ifdef M4D_DEV
   // development build only: m4d_dev_set_flags(0x100 | (MODE << 4) | PP) selects a measured variant
   if (g_dev_flags & 0x100) {
     const int pp = g_dev_flags & 0xF, mode = (g_dev_flags >> 4) & 3;
+    persist = false;
     if (mode == 2) {
       kern = pp == 0 ? attn_fwd_d128_kernel<0, 2> : pp == 1 ? attn_fwd_d128_kernel<1, 2>
            : pp == 2 ? attn_fwd_d128_kernel<2, 2> : pp == 3 ? attn_fwd_d128_kernel<3, 2> : attn_fwd_d128_kernel<4, 2>;
@@ -890,7 +1000,10 @@ static int attention_impl(const void* q, const void* k, const void* v, void* out
   p.seg_tiles = seg_len / A_BKV;
   p.scatter_rows = n_scatter > 0 ? scatter_rows : 0;
   for (int i = 0; i < 8; ++i) p.out_scatter[i] = i < n_scatter ? static_cast<bf16*>(out_scatter[i]) : nullptr;
-  dim3 grid((Lq + A_NQ * A_BQ - 1) / (A_NQ * A_BQ), heads, B);
+  p.n_qblk = n_qblk;
+  p.n_items = static_cast<int>(n_items < (1ll << 30) ? n_items : 0);
+  dim3 grid(n_qblk, heads, B);
+  if (persist) grid = dim3(sm_count(), 1, 1);
   kern<<<grid, threads, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
   M4D_CHECK_LAUNCH("attn_fwd_d128_kernel");
   return M4D_OK;

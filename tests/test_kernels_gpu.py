@@ -241,6 +241,36 @@ def test_attention_two_segments_one_launch(ops, B, Lq, seg, Lk):
         ops.attention_seg2(qg, kg, vg, seg + 1)
 
 
+@pytest.mark.parametrize("Lk,seg", [(769, 512), (300, 0), (128, 0), (2048, 1024)])
+def test_attention_persistent_ctas_short_key_ranges(ops, Lk, seg):
+    """Key ranges up to 2048 with more work items than SMs run on PERSISTENT CTAs (one per SM looping
+    over (q block, head, batch) items, barrier phases on running counters).  Rows are independent,
+    so the result must be BIT-IDENTICAL to the same queries launched in chunks small enough for the
+    one-CTA-per-item kernel (<= 148 items), and match the oracle."""
+    B, Lq, N = 2, 2560 + 77, 8                       # 11 q blocks x 8 heads x 2 = 176 items > 148 SMs
+    q = _rand((B, Lq, N, 128), 81)
+    k = _rand((B, Lk, N, 128), 82)
+    v = _rand((B, Lk, N, 128), 83)
+    qg, kg, vg = q.cuda(), k.cuda(), v.cuda()
+    run = (lambda qq: ops.attention_seg2(qq, kg, vg, seg)) if seg else (lambda qq: ops.attention(qq, kg, vg))
+    big = run(qg)
+    parts = torch.cat([run(qg[:, a:a + 1024].contiguous()) for a in range(0, Lq, 1024)], dim=1)   # 4 x 8 x 2 = 64 items
+    assert torch.equal(big, parts)
+    ar = O.Arith(True)
+    rows = slice(1500, 1500 + 300)                   # oracle on a slice of the queries (cost)
+    if seg:
+        ref = ar.r(O.attention(q[:, rows], k[:, :seg], v[:, :seg], None, ar) +
+                   O.attention(q[:, rows], k[:, seg:], v[:, seg:], None, ar))
+    else:
+        ref = O.attention(q[:, rows], k, v, None, ar)
+    assert rel_err(big[:, rows].float().cpu(), ref) < 6e-3
+    if not seg:                                      # accumulate form on persistent CTAs
+        acc = big.clone()
+        ops.attention(qg, kg, vg, out=acc, accumulate=True)
+        two = ar.r(big.float().cpu() * 2)
+        assert rel_err(acc.float().cpu(), two) < 1e-2
+
+
 def test_attention_rejects_head_dim(ops):
     q = _rand((1, 64, 2, 64), 1).cuda()
     with pytest.raises(RuntimeError):
