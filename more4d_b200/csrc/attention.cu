@@ -707,7 +707,7 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float l0 = 0.f, l1 = 0.f;
       if (MODE == 1) {
         float neg_mc = -m_used * c;
-        bool exact = true;                         // a segment's first tile has no reference to speculate with
+        bool exact = false;
         if (__builtin_expect(!first, 1)) {
           // ---- first half, speculative
           tmem_ld32(tS + 0, s + 0);
@@ -734,22 +734,39 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           exp_pipe<PP, 16, 16>(s, ph + 16, c, neg_mc, l0, l1);
           exact = __any_sync(0xffffffffu, !(l0 + l1 < A_SUM_GUARD));
         } else {
-          // (the exact path below loads the first half itself; the second half is taken from here)
+          // a segment's first tile: the whole tile in one TMEM read, row max from registers (the
+          // textbook order), first half's exponentials; O and l start from zero
+          tmem_ld32(tS + 0, s + 0);
+          tmem_ld32(tS + 32, s + 32);
           tmem_ld32(tS + 64, s + 64);
           tmem_ld32(tS + 96, s + 96);
           tmem_ld_wait();
+          reg_fence32(s + 0);
+          reg_fence32(s + 32);
           reg_fence32(s + 64);
           reg_fence32(s + 96);
-          if (__builtin_expect(valid < A_BKV, 0)) {
+          if (valid < A_BKV) {
 #pragma unroll
-            for (int i = 64; i < 128; ++i)
+            for (int i = 0; i < 128; ++i)
               if (i >= valid) s[i] = 0xFF800000u;
           }
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 128; i += 8) {
+            mx[0] = max3(mx[0], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx[1] = max3(mx[1], __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            mx[2] = max3(mx[2], __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+            mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+          }
+          m_used = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          l_sum = 0.f;
+          neg_mc = -m_used * c;
+          exp_pipe<PP, 0, 32>(s, ph, c, neg_mc, l0, l1);
         }
         if (__builtin_expect(exact, 0)) {
           // exact path for the whole tile: S is intact (nothing of this tile has been stored);
           // "S_t(j) ready" implies PV_t(j-1) has finished, so O may be rescaled
-          const bool mine = first || !(l0 + l1 < A_SUM_GUARD);
+          const bool mine = !(l0 + l1 < A_SUM_GUARD);
           float mxr = -INFINITY;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
@@ -761,11 +778,11 @@ attn_fwd_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           float f = 1.0f;
           if (mine) {
             const float m_new = fmaxf(m_used, mxr);
-            f = first ? 0.f : fast_exp2((m_used - m_new) * c);
+            f = fast_exp2((m_used - m_new) * c);
             m_used = m_new;
             l_sum *= f;
           }
-          if (!first) rescale_o(f);                // warp-collective tcgen05 ops: every lane takes part
+          rescale_o(f);                            // warp-collective tcgen05 ops: every lane takes part
           neg_mc = -m_used * c;
           tmem_ld32(tS + 0, s + 0);
           tmem_ld32(tS + 32, s + 32);
