@@ -256,3 +256,21 @@ def test_fused_peer_exchange_addressing(rec):
     assert qs == (B, L, h, d) and ks == qs
     assert outs == [((B, n_loc, h, d), (n_loc * C, C, d, 1), r * h * d)] * P
     assert rec.calls["rmsnorm_rope_+rope"] == 2                      # RoPE after the exchange, on my heads
+
+
+def test_cross_attention_key_buffer_adjacency():
+    """WanI2VCrossAttention keeps text keys then image keys in ONE buffer and hands out views; `attend` runs
+    both softmaxes in one launch (ops.attention_seg2) only when the views really are adjacent slices of one
+    [B, Lt + Li, C] buffer with Lt a multiple of the 128-key tile — also after the cfg_skip batch slicing —
+    and falls back to two launches for anything else."""
+    adj = dit_mod.WanI2VCrossAttention._adjacent
+    kc = torch.randn(2, 512 + 257, 256).to(BF16)
+    k, ki = kc[:, :512], kc[:, 512:]
+    assert adj(k, ki)
+    assert adj(k[1:], ki[1:])                                    # conditional half of a CFG batch (Conditioning.tail)
+    assert not adj(k.contiguous(), ki.contiguous())              # separate tensors
+    assert not adj(ki, k)                                        # wrong order
+    k77, ki77 = torch.randn(2, 77 + 257, 256).to(BF16).split([77, 257], dim=1)
+    assert not adj(k77, ki77)                                    # first segment not a multiple of 128 keys
+    other = torch.randn(2, 512 + 257, 256).to(BF16)
+    assert not adj(k, other[:, 512:])                            # views of different buffers
