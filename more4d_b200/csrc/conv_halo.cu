@@ -86,8 +86,9 @@ __device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint32_t a_l
 // exposed: 7.4 ms of a 23.6 ms launch at 49x360x640 before the split (profiles/conv_fused_r02.md).
 // TMEM loads are double-buffered (chunk c+1 is in flight while chunk c is processed; the
 // single-buffered version spent 40 % of its samples on the TMEM / residual scoreboards), all
-// bf16 arithmetic is packed (ptx.cuh), and the epilogue warps run with 224 registers
-// (setmaxnreg) to hold 96 packed words + two 32-word TMEM chunks + two residual chunks.
+// bf16 arithmetic is packed (ptx.cuh), and the epilogue warps run with 208 registers
+// (setmaxnreg; producers / issuer 80) to hold up to 96 packed words + two TMEM chunks + two
+// residual chunks.
 template <int NTC, bool NORM>
 __device__ __forceinline__ float drain_pass1(const ConvParams& p, uint32_t t_row, long long pix_off, int n0,
                                              bool pix_ok, bool has_res, uint4* rnext, uint32_t* yp) {
