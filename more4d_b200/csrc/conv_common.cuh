@@ -195,11 +195,13 @@ __device__ __forceinline__ void conv_store_chunk(const ConvParams& p, const uint
     const int fo = t * p.t_mul + p.t_off + n0 / p.n_split;
     const int ch = n0 % p.n_split;
     const long long off = ((static_cast<long long>(fo) * p.H_out + h) * p.W_out + w) * p.out_C + ch;
-    float v[32];
     uint4 r4[4];
+    uint32_t y[16];
+    const bool a32 = ((reinterpret_cast<uintptr_t>(p.out) + 2 * off) & 31) == 0;    // whole 32-byte sectors
     if (p.residual != nullptr) load_res_chunk(p.residual + off, r4);
-    conv_chunk_values(rr, p.bias ? p.bias + n0 : nullptr, p.residual ? r4 : nullptr, v);
-    store_chunk_bf16(reinterpret_cast<bf16*>(p.out) + off, v);
+    conv_chunk_packed(rr, p.bias ? p.bias + n0 : nullptr, p.residual ? r4 : nullptr, y);
+    if (a32) store_chunk_packed32(reinterpret_cast<bf16*>(p.out) + off, y);
+    else store_chunk_packed(reinterpret_cast<bf16*>(p.out) + off, y);
   } else {
     conv_store_chunk_slow(p, rr, t, h, w, n0);
   }
