@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_vae_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | tail -4) > gpurun_out/pytest_k.log
-cat gpurun_out/pytest_k.log
-timeout 300 python tools/vae_trace.py > gpurun_out/vae_trace_r02k.md 2> gpurun_out/vae_trace.err
-head -8 gpurun_out/vae_trace_r02k.md | tail -4; grep "(1,3,3) (0,0,0)\|(3,1,1)" gpurun_out/vae_trace_r02k.md
+rm -f gpurun_out/bench_r02_other_workloads.jsonl
+for w in 480p-14b 720p-1.3b 480p-1.3b visim-368p-14b; do
+  timeout 400 python bench.py --workload $w --no-cpu-baseline --no-vae 2> gpurun_out/other_$w.err >> gpurun_out/bench_r02_other_workloads.jsonl
+  tail -1 gpurun_out/other_$w.err | cut -c1-200
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/bench_r02_other_workloads.jsonl'):
+    d=json.loads(l); print(d['config']['workload'][:40], round(d['value'],4), round(d['ms_per_step'],1), round(d['roofline']['frac'],3), round(d['kernel_class_ms']['cross_attention'],1))
+PY
